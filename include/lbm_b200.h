@@ -1,0 +1,149 @@
+/*
+ * lbm_b200.h -- C-ABI of the B200-native D2Q9-BGK timestep path (liblbm_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of ag14774/MPILattice-Boltzmann: everything
+ * the reference's main() does between `tic` and `toc` (d2q9-bgk.c:278-398) plus the state it
+ * hands to calc_reynolds/write_values afterwards.  The reference has no plugin or FFI layer;
+ * each entry point below cites the internal reference interface it replaces.  Plain pointers
+ * and sizes only -- no CUDA, torch or C++ types cross this boundary.
+ *
+ * Data contract (same as the reference):
+ *   cells      array-of-structs, 9 floats per cell in the reference's speed order
+ *              (d2q9-bgk.c:7-13, 95-98), row-major, row 0 first: cells[(y*nx + x)*9 + k]
+ *   obstacles  one int per cell, 0 = fluid, non-zero = blocked (d2q9-bgk.c:875, 905-911)
+ *   av_vels    one float per timestep (d2q9-bgk.c:367, 396)
+ * Inside the library the populations live as 9 fp32 planes (structure of arrays) and the
+ * obstacle map as 1 bit per cell; see DESIGN.md.
+ *
+ * Error convention: every function returning int returns LBM_B200_OK (0) or a non-zero code;
+ * lbm_b200_last_error() then describes the failure (thread-local).  The reference's
+ * convention is die(message, __LINE__, __FILE__) (d2q9-bgk.c:1145-1151): the host program
+ * passes lbm_b200_last_error() to its own die().  There is no CPU fallback: without a usable
+ * CUDA device every compute entry point fails with LBM_B200_ERR_CUDA.
+ *
+ * Threading: a handle is driven by one host thread at a time.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+enum {
+  LBM_B200_OK = 0,
+  LBM_B200_ERR_ARG = 1,      /* bad argument (sizes, NULL, unsupported shape) */
+  LBM_B200_ERR_CUDA = 2,     /* CUDA runtime / driver failure, or no device */
+  LBM_B200_ERR_ALLOC = 3,    /* host or device allocation failed */
+  LBM_B200_ERR_STATE = 4     /* call not valid in the handle's current state */
+};
+
+typedef struct lbm_b200 lbm_b200;   /* opaque: owns device memory, streams, graphs */
+
+/* ---- host-only helpers (usable without a GPU) ------------------------------------- */
+
+int lbm_b200_abi_version(void);
+
+/* Row-slab decomposition of ny rows over n_slabs, replacing d2q9-bgk.c:834-862: ny/n rows
+ * each, the remainder one per slab from slab 0, and the last slab never thinner than 3 rows
+ * (the accelerated row ny-2 must not be an exchanged edge row).  rows[] and first_row[] have
+ * n_slabs entries.  Fails if any slab would get fewer than 3 rows. */
+int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row);
+
+/* 1.0f / (number of unblocked cells), replacing d2q9-bgk.c:805, 945-950. */
+float lbm_b200_free_cells_inv(const int* obstacles, long n_cells);
+
+const char* lbm_b200_last_error(void);
+
+/* Number of visible CUDA devices (0 if there is none or the driver is missing). */
+int lbm_b200_device_count(void);
+
+/* ---- whole-domain solver in one process -------------------------------------------- */
+
+/* Replaces the device-independent part of initialise() (d2q9-bgk.c:865-902, 966-970):
+ * allocates the two population buffers, fills them with the uniform initial state
+ * w0 = 4/9 rho, w1 = rho/9, w2 = rho/36, uploads the bit-packed obstacle map and splits the
+ * grid into n_slabs row slabs (lbm_b200_decompose).  devices[i] is the CUDA device of slab i
+ * (NULL: slab i on device i).  Slabs on different devices exchange halo rows with direct
+ * NVLink stores; several slabs may share one device (then they run in lock step on one
+ * stream -- used to test the exchange on a single GPU).
+ * Requires nx >= 4, ny >= 3. */
+int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                    const int* obstacles, int n_slabs, const int* devices);
+
+/* ---- one slab per process (one rank per GPU; ranks launched by torchrun or similar) --- */
+
+/* As lbm_b200_create, for the slab [first_row, first_row + rows) of a ny_global-row grid owned
+ * by `rank` of `n_ranks` (ring neighbours rank-1 and rank+1, as d2q9-bgk.c:244-247).
+ * obstacles_slab holds this slab's rows only (the reference's MPI_Scatterv, 968-970) and
+ * free_cells_inv is the global value (the reference's MPI_Bcast, 966). */
+int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                         int rank, int n_ranks, float density, float accel, float omega,
+                         float free_cells_inv, const int* obstacles_slab, int device);
+
+/* Size in bytes of the blob written by lbm_b200_ipc_export. */
+int lbm_b200_ipc_blob_bytes(void);
+
+/* Writes this slab's CUDA IPC handles (population buffers + flag words) so that the two ring
+ * neighbours can map them.  Replaces MPI_Recv_init/MPI_Send_init (d2q9-bgk.c:295-313). */
+int lbm_b200_ipc_export(lbm_b200* handle, void* blob);
+
+/* Maps the neighbours' buffers.  `south` is the blob of rank-1 (owner of the rows below this
+ * slab), `north` that of rank+1; with 2 ranks both are the same rank's blob.  Collective in
+ * spirit: every rank must call it before any rank runs. */
+int lbm_b200_ipc_connect(lbm_b200* handle, const void* south_blob, const void* north_blob);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+
+/* Advances the state by `iters` timesteps, replacing the loop d2q9-bgk.c:315-394 (halo
+ * exchange, accelerate_flow, timestep on interior and edge rows, per-step average, buffer
+ * swap) and the final reduction (396).  All steps are enqueued without host synchronisation;
+ * one synchronisation and one device-to-host copy happen at the end.
+ * av_vels (host, `iters` floats, may be NULL) receives, per step,
+ *   (float)(Sigma over this handle's free cells of |m|/rho) * free_cells_inv
+ * i.e. the reference's av_vels_local[tt] (367); for a whole-domain handle that is the final
+ * av_vels[tt], for a slab handle the ranks' arrays are summed element-wise as in (396). */
+int lbm_b200_run(lbm_b200* handle, int iters, float* av_vels);
+
+/* The same work split for device-side timing: enqueue returns at once, sync blocks, and
+ * elapsed_ms reports the CUDA-event time of the last enqueue's timestep kernels (maximum
+ * over the handle's devices); fetch copies the per-step averages of the last enqueue. */
+int lbm_b200_enqueue(lbm_b200* handle, int iters);
+int lbm_b200_sync(lbm_b200* handle);
+int lbm_b200_elapsed_ms(lbm_b200* handle, float* ms);
+int lbm_b200_fetch_av_vels(lbm_b200* handle, int iters, float* av_vels);
+
+/* ---- state in and out -------------------------------------------------------------- */
+
+/* Rows owned by the handle: the whole grid, or the slab.  Any pointer may be NULL. */
+int lbm_b200_shape(const lbm_b200* handle, int* nx, int* rows, int* first_row);
+
+/* Current populations in the reference's AoS layout, rows*nx*9 floats (what main() hands to
+ * calc_reynolds/write_values, d2q9-bgk.c:408, 420). */
+int lbm_b200_get_cells(lbm_b200* handle, float* cells);
+
+/* Overwrites the populations (rows*nx*9 floats, AoS).  Not in the reference; lets tests start
+ * from arbitrary states. */
+int lbm_b200_set_cells(lbm_b200* handle, const float* cells);
+
+/* Macroscopic fields of the current state, computed on the device exactly as write_values
+ * does (d2q9-bgk.c:1076-1111): four arrays of rows*nx floats.  Blocked cells give
+ * u_x = u_y = u = 0 and pressure = density/3.  Any pointer may be NULL. */
+int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u, float* pressure);
+
+/* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
+ *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit)
+ *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches)
+ *   "ctas_per_sm"   persistent-grid size in CTAs per SM (0 = occupancy query)
+ */
+int lbm_b200_set_option(lbm_b200* handle, const char* key, long value);
+int lbm_b200_get_option(const lbm_b200* handle, const char* key, long* value);
+
+void lbm_b200_destroy(lbm_b200* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

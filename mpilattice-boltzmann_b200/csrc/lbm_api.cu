@@ -1,0 +1,868 @@
+// lbm_api.cu -- implementation of include/lbm_b200.h: slab bookkeeping, launches, halo wiring.
+//
+// Host-side structure of the reference's timed region (d2q9-bgk.c:278-398), re-designed for
+// B200: no host synchronisation inside the step loop, one persistent-grid kernel launch per
+// slab region per step, halo rows pushed over NVLink by the edge-row kernel itself, per-step
+// averages reduced on the device and copied back once.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <unistd.h>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess)                                                                 \
+      return fail(LBM_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+enum FlagWord { kFromSouth = 0, kFromNorth = 1, kEpoch = 2, kDone = 3, kFlagWords = 32 };
+
+struct Neighbour {
+  float* buf[2] = {nullptr, nullptr};   // the neighbour's two population buffers (peer or IPC mapped)
+  unsigned* flags = nullptr;            // the neighbour's flag words
+  size_t plane = 0;
+  int rows = 0;
+  bool ipc = false;                     // mapped with cudaIpcOpenMemHandle (must be closed)
+};
+
+struct Slab {
+  int device = 0;
+  int rows = 0, first_row = 0;
+  size_t plane = 0;
+  float* buf[2] = {nullptr, nullptr};
+  uint32_t* mask = nullptr;
+  unsigned* flags = nullptr;
+  double* partials = nullptr;
+  float* av_dev = nullptr;
+  size_t av_cap = 0;
+  unsigned* cursor = nullptr;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  Neighbour south, north;
+  int accel_row = -1;                   // padded row of global row ny-2, or -1 if another slab owns it
+  // launch geometry
+  int threads_full = 256, grid_full = 1;
+  int threads_edge = 256, grid_edge = 0;
+  int threads_int = 256, grid_int = 0;
+  int per_step = 1;
+  std::vector<cudaGraphExec_t> graphs;  // [parity]
+};
+
+struct IpcBlob {
+  cudaIpcMemHandle_t buf[2];
+  cudaIpcMemHandle_t flags;
+  unsigned long long plane;
+  int rows;
+  int device;
+  int pid;
+};
+
+constexpr int kChunkSteps = 256;        // steps whose CTA partials are kept before one reduce launch
+
+}  // namespace
+
+struct lbm_b200 {
+  int nx = 0, ny = 0;
+  float density = 0, accel = 0, omega = 0, inv = 0;
+  lbm::StepConst sc{};
+  int mask_row_words = 0;
+  int n_ranks = 1;                      // slabs in the ring (all processes)
+  int rank0 = 0;                        // ring index of slabs[0]
+  bool multi_process = false;
+  bool connected = true;
+  int cur = 0;                          // index of the buffer holding the current state
+  std::vector<Slab> slabs;
+  // options
+  long opt_kernel = 0, opt_graph_steps = 0, opt_ctas_per_sm = 0, opt_min_ctas = 2;
+  int last_iters = 0;
+  int graph_len = 0;
+  long launches = 0;                    // kernels launched by the last enqueue (all slabs)
+};
+
+namespace {
+
+using lbm::StepArgs;
+
+bool use_vec4(const lbm_b200* h)
+{
+  const bool ok = (h->nx % 4 == 0) && h->nx >= 8;
+  if (h->opt_kernel == 1) return false;
+  return ok;
+}
+
+template <typename K>
+int occupancy(K kernel, int threads)
+{
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
+// persistent-grid geometry for `rows` rows of the slab
+void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* grid)
+{
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (rows <= 0) { *threads = 256; *grid = 0; return; }
+  if (use_vec4(h)) {
+    const long nseg = (long)rows * ((h->nx + lbm::kSegCells - 1) / lbm::kSegCells);
+    long warps = (nseg + sms - 1) / sms;             // spread small grids over the SMs
+    warps = std::max(1L, std::min(8L, warps));
+    *threads = (int)warps * 32;
+    int per_sm = (int)h->opt_ctas_per_sm;
+    if (per_sm <= 0) {
+      per_sm = (h->opt_min_ctas >= 3) ? occupancy(lbm::step_vec4<false, 3>, *threads)
+                                      : occupancy(lbm::step_vec4<false, 2>, *threads);
+    }
+    const long want = (nseg + warps - 1) / warps;
+    *grid = (int)std::max(1L, std::min(want, (long)sms * per_sm));
+  } else {
+    const long ncell = (long)rows * h->nx;
+    *threads = 256;
+    int per_sm = (int)h->opt_ctas_per_sm;
+    if (per_sm <= 0) per_sm = occupancy(lbm::step_scalar<false>, 256);
+    const long want = (ncell + 255) / 256;
+    *grid = (int)std::max(1L, std::min(want, (long)sms * per_sm));
+  }
+}
+
+void plan(lbm_b200* h)
+{
+  for (Slab& s : h->slabs) {
+    if (h->n_ranks == 1) {
+      plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
+      s.grid_edge = s.grid_int = 0;
+      s.per_step = s.grid_full;
+    } else {
+      plan_region(h, s.device, 2, &s.threads_edge, &s.grid_edge);
+      plan_region(h, s.device, s.rows - 2, &s.threads_int, &s.grid_int);
+      s.grid_full = 0;
+      s.per_step = s.grid_edge + s.grid_int;
+    }
+  }
+}
+
+void destroy_graphs(lbm_b200* h)
+{
+  for (Slab& s : h->slabs) {
+    for (cudaGraphExec_t g : s.graphs)
+      if (g) cudaGraphExecDestroy(g);
+    s.graphs.clear();
+  }
+  h->graph_len = 0;
+}
+
+int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
+{
+  CUDA_TRY(cudaSetDevice(s.device));
+  s.plane = (size_t)(s.rows + 2) * h->nx;
+  const size_t bytes = 9 * s.plane * sizeof(float);
+  for (int b = 0; b < 2; b++) {
+    cudaError_t e = cudaMalloc(&s.buf[b], bytes);
+    if (e != cudaSuccess)
+      return fail(LBM_B200_ERR_ALLOC, "cudaMalloc of %zu bytes for populations failed: %s", bytes, cudaGetErrorString(e));
+  }
+  CUDA_TRY(cudaMalloc(&s.flags, kFlagWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.flags, 0, kFlagWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&s.cursor, sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.cursor, 0, sizeof(unsigned)));
+  CUDA_TRY(cudaEventCreate(&s.ev_start));
+  CUDA_TRY(cudaEventCreate(&s.ev_stop));
+
+  // bit-pack the obstacle rows: 32 cells per word, rows padded to whole words
+  const size_t words = (size_t)s.rows * h->mask_row_words;
+  std::vector<uint32_t> packed(words, 0u);
+  for (int r = 0; r < s.rows; r++) {
+    const int* row = obstacles_rows + (size_t)r * h->nx;
+    uint32_t* out = packed.data() + (size_t)r * h->mask_row_words;
+    for (int x = 0; x < h->nx; x++)
+      if (row[x]) out[x >> 5] |= 1u << (x & 31);
+  }
+  CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(s.mask, packed.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+  // uniform initial state in both buffers, halo rows included (d2q9-bgk.c:880-902)
+  const float w0 = h->density * 4.0f / 9.0f, w1 = h->density / 9.0f, w2 = h->density / 36.0f;
+  const unsigned blocks = (unsigned)((s.plane + 255) / 256);
+  for (int b = 0; b < 2; b++) lbm::fill_planes<<<blocks, 256, 0, s.stream>>>(s.buf[b], s.plane, w0, w1, w2);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+
+  const int accel_global = h->ny - 2;
+  s.accel_row = (accel_global >= s.first_row && accel_global < s.first_row + s.rows) ? accel_global - s.first_row + 1 : -1;
+  return LBM_B200_OK;
+}
+
+int ensure_av_capacity(Slab& s, size_t iters)
+{
+  const size_t need = std::max<size_t>(iters, 1);
+  if (s.av_cap >= need) return LBM_B200_OK;
+  CUDA_TRY(cudaSetDevice(s.device));
+  if (s.av_dev) CUDA_TRY(cudaFree(s.av_dev));
+  s.av_dev = nullptr;
+  CUDA_TRY(cudaMalloc(&s.av_dev, need * sizeof(float)));
+  s.av_cap = need;
+  return LBM_B200_OK;
+}
+
+int ensure_partials(lbm_b200* h)
+{
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    if (s.partials) CUDA_TRY(cudaFree(s.partials));
+    s.partials = nullptr;
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)kChunkSteps * s.per_step * sizeof(double)));
+  }
+  return LBM_B200_OK;
+}
+
+StepArgs base_args(const lbm_b200* h, const Slab& s, int slot, bool fold_accel)
+{
+  StepArgs a{};
+  a.src = s.buf[h->cur];
+  a.dst = s.buf[h->cur ^ 1];
+  a.plane = s.plane;
+  a.mask = s.mask;
+  a.mask_row_words = h->mask_row_words;
+  a.nx = h->nx;
+  a.chunks = (h->nx + lbm::kSegCells - 1) / lbm::kSegCells;
+  a.row_first = 1;
+  a.row_last = s.rows;
+  a.accel_row = fold_accel ? s.accel_row : -1;
+  a.c = h->sc;
+  a.partials = s.partials + (size_t)slot * s.per_step;
+  return a;
+}
+
+template <bool PEER>
+int launch_step(lbm_b200* h, const Slab& s, const StepArgs& a, int grid, int threads)
+{
+  if (grid <= 0) return LBM_B200_OK;
+  h->launches++;
+  if (use_vec4(h)) {
+    if (h->opt_min_ctas >= 3) lbm::step_vec4<PEER, 3><<<grid, threads, 0, s.stream>>>(a);
+    else lbm::step_vec4<PEER, 2><<<grid, threads, 0, s.stream>>>(a);
+  } else {
+    lbm::step_scalar<PEER><<<grid, threads, 0, s.stream>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return LBM_B200_OK;
+}
+
+// One timestep on every slab of this handle: d2q9-bgk.c:326-378.
+int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
+{
+  if (h->n_ranks == 1) {
+    Slab& s = h->slabs[0];
+    CUDA_TRY(cudaSetDevice(s.device));
+    StepArgs a = base_args(h, s, slot, fold_accel);
+    a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+    a.south_of_first = s.rows;          // periodic wrap in y without halo copies
+    a.north_of_last = 1;
+    int rc = launch_step<false>(h, s, a, s.grid_full, s.threads_full);
+    if (rc) return rc;
+  } else {
+    // edge rows first: they wait for the neighbours' previous edge rows, push this state's
+    // halo rows over NVLink and signal; the interior then runs while the neighbours consume.
+    for (Slab& s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      StepArgs a = base_args(h, s, slot, fold_accel);
+      a.row_begin = 1; a.row_count = 2; a.row_stride = s.rows - 1;
+      a.south_of_first = 0;
+      a.north_of_last = s.rows + 1;
+      a.north_dst = s.north.buf[h->cur ^ 1]; a.north_plane = s.north.plane; a.north_row = 0;
+      a.south_dst = s.south.buf[h->cur ^ 1]; a.south_plane = s.south.plane; a.south_row = s.south.rows + 1;
+      a.wait_from_south = s.flags + kFromSouth;
+      a.wait_from_north = s.flags + kFromNorth;
+      a.signal_north = s.north.flags + kFromSouth;   // I am my northern neighbour's south
+      a.signal_south = s.south.flags + kFromNorth;
+      a.epoch = s.flags + kEpoch;
+      a.done = s.flags + kDone;
+      int rc = launch_step<true>(h, s, a, s.grid_edge, s.threads_edge);
+      if (rc) return rc;
+    }
+    for (Slab& s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      StepArgs a = base_args(h, s, slot, fold_accel);
+      a.row_begin = 2; a.row_count = s.rows - 2; a.row_stride = 1;
+      a.south_of_first = 0;
+      a.north_of_last = s.rows + 1;
+      a.partials += s.grid_edge;
+      int rc = launch_step<false>(h, s, a, s.grid_int, s.threads_int);
+      if (rc) return rc;
+    }
+  }
+  h->cur ^= 1;
+  return LBM_B200_OK;
+}
+
+int enqueue_reduce(lbm_b200* h, int steps)
+{
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const int blocks = (steps * 32 + 255) / 256;
+    lbm::reduce_partials<<<blocks, 256, 0, s.stream>>>(s.partials, s.per_step, steps, h->inv, s.av_dev, s.cursor);
+    lbm::advance_cursor<<<1, 1, 0, s.stream>>>(s.cursor, (unsigned)steps);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+  }
+  return LBM_B200_OK;
+}
+
+// Captures `len` steps (+ their reduce) into one CUDA graph per slab, for both buffer parities.
+int build_graphs(lbm_b200* h, int len)
+{
+  destroy_graphs(h);
+  if (h->slabs.size() != 1 || h->n_ranks != 1)
+    return fail(LBM_B200_ERR_STATE, "graph_steps is supported for single-slab handles only");
+  Slab& s = h->slabs[0];
+  CUDA_TRY(cudaSetDevice(s.device));
+  const int cur0 = h->cur;
+  s.graphs.assign(2, nullptr);
+  for (int parity = 0; parity < 2; parity++) {
+    h->cur = parity;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LBM_B200_OK;
+    for (int t = 0; t < len && rc == LBM_B200_OK; t++) rc = enqueue_step(h, t, true);
+    if (rc == LBM_B200_OK) rc = enqueue_reduce(h, len);
+    cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+    if (rc != LBM_B200_OK) { if (graph) cudaGraphDestroy(graph); h->cur = cur0; return rc; }
+    if (e != cudaSuccess) { h->cur = cur0; return fail(LBM_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(&s.graphs[parity], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->cur = cur0; return fail(LBM_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+  }
+  h->cur = cur0;
+  h->graph_len = len;
+  return LBM_B200_OK;
+}
+
+int finish_create(lbm_b200* h)
+{
+  plan(h);
+  return ensure_partials(h);
+}
+
+int check_common(int nx, int ny, float omega, const void* obstacles, lbm_b200** handle)
+{
+  if (!handle) return fail(LBM_B200_ERR_ARG, "handle pointer is NULL");
+  *handle = nullptr;
+  if (!obstacles) return fail(LBM_B200_ERR_ARG, "obstacles pointer is NULL");
+  if (nx < 4 || ny < 3) return fail(LBM_B200_ERR_ARG, "grid %dx%d too small (need nx >= 4, ny >= 3)", nx, ny);
+  if (!(omega > 0.0f)) return fail(LBM_B200_ERR_ARG, "omega must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(LBM_B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  return LBM_B200_OK;
+}
+
+void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float omega, float inv)
+{
+  h->nx = nx; h->ny = ny;
+  h->density = density; h->accel = accel; h->omega = omega; h->inv = inv;
+  h->sc.omega = omega;
+  h->sc.aw1 = density * accel * 0.111111111111111111111111f;    // d2q9-bgk.c:445
+  h->sc.aw2 = density * accel * 0.0277777777777777777777778f;   // d2q9-bgk.c:446
+  h->mask_row_words = (nx + 31) / 32;
+  if (const char* e = getenv("LBM_B200_KERNEL")) h->opt_kernel = atol(e);
+  if (const char* e = getenv("LBM_B200_GRAPH_STEPS")) h->opt_graph_steps = atol(e);
+  if (const char* e = getenv("LBM_B200_CTAS_PER_SM")) h->opt_ctas_per_sm = atol(e);
+  if (const char* e = getenv("LBM_B200_MIN_CTAS")) h->opt_min_ctas = atol(e);
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int lbm_b200_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+const char* lbm_b200_last_error(void) { return g_error.c_str(); }
+
+int lbm_b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row)
+{
+  if (ny < 1 || n_slabs < 1 || !rows || !first_row) return fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_decompose");
+  const int base = ny / n_slabs;
+  int extra = ny % n_slabs;
+  int grow_last = 0, shrink_second_to_last = 0;
+  if (base < 3) {                      // keep the last slab at >= 3 rows (see header)
+    grow_last = 1;
+    if (extra) extra--;
+    else shrink_second_to_last = 1;
+  }
+  int next = 0;
+  for (int i = 0; i < n_slabs; i++) {
+    int r = base + (i < extra ? 1 : 0);
+    if (i == n_slabs - 2) r -= shrink_second_to_last;
+    if (i == n_slabs - 1) r += grow_last;
+    rows[i] = r;
+    first_row[i] = next;
+    next += r;
+  }
+  for (int i = 0; i < n_slabs; i++)
+    if (rows[i] < 3 && n_slabs > 1)
+      return fail(LBM_B200_ERR_ARG, "slab %d of %d would have %d rows; at least 3 rows per slab are required", i, n_slabs, rows[i]);
+  return LBM_B200_OK;
+}
+
+float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
+{
+  long free_cells = n_cells;
+  for (long i = 0; i < n_cells; i++)
+    if (obstacles[i]) free_cells--;
+  return 1.0f / free_cells;
+}
+
+int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                    const int* obstacles, int n_slabs, const int* devices)
+{
+  int rc = check_common(nx, ny, omega, obstacles, handle);
+  if (rc) return rc;
+  if (n_slabs < 1) return fail(LBM_B200_ERR_ARG, "n_slabs must be >= 1");
+  std::vector<int> rows(n_slabs), first(n_slabs);
+  rc = lbm_b200_decompose(ny, n_slabs, rows.data(), first.data());
+  if (rc) return rc;
+  int ndev = 0;
+  cudaGetDeviceCount(&ndev);
+
+  lbm_b200* h = new lbm_b200();
+  init_common(h, nx, ny, density, accel, omega, lbm_b200_free_cells_inv(obstacles, (long)nx * ny));
+  h->n_ranks = n_slabs;
+  h->slabs.resize(n_slabs);
+  for (int i = 0; i < n_slabs; i++) {
+    Slab& s = h->slabs[i];
+    s.device = devices ? devices[i] : i;
+    s.rows = rows[i];
+    s.first_row = first[i];
+    if (s.device < 0 || s.device >= ndev) {
+      lbm_b200_destroy(h);
+      return fail(LBM_B200_ERR_ARG, "slab %d asks for device %d but %d device(s) are visible", i, s.device, ndev);
+    }
+  }
+  // one stream per device; slabs that share a device share its stream (lock step)
+  for (int i = 0; i < n_slabs; i++) {
+    Slab& s = h->slabs[i];
+    for (int j = 0; j < i; j++)
+      if (h->slabs[j].device == s.device) { s.stream = h->slabs[j].stream; break; }
+    if (!s.stream) {
+      if (cudaSetDevice(s.device) != cudaSuccess || cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        lbm_b200_destroy(h);
+        return fail(LBM_B200_ERR_CUDA, "cannot create a stream on device %d: %s", s.device, cudaGetErrorString(cudaGetLastError()));
+      }
+      s.own_stream = true;
+    }
+  }
+  for (int i = 0; i < n_slabs; i++) {
+    rc = alloc_slab(h, h->slabs[i], obstacles + (size_t)first[i] * nx);
+    if (rc) { lbm_b200_destroy(h); return rc; }
+  }
+  // ring wiring: direct peer pointers (d2q9-bgk.c:244-247 for the neighbour ranks)
+  if (n_slabs > 1) {
+    for (int i = 0; i < n_slabs; i++) {
+      Slab& s = h->slabs[i];
+      Slab& so = h->slabs[(i - 1 + n_slabs) % n_slabs];
+      Slab& no = h->slabs[(i + 1) % n_slabs];
+      for (Slab* o : {&so, &no}) {
+        if (o->device == s.device) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, s.device, o->device);
+        if (!can) { lbm_b200_destroy(h); return fail(LBM_B200_ERR_CUDA, "device %d cannot access peer device %d", s.device, o->device); }
+        cudaSetDevice(s.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          lbm_b200_destroy(h);
+          return fail(LBM_B200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", s.device, o->device, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+      }
+      s.south.buf[0] = so.buf[0]; s.south.buf[1] = so.buf[1]; s.south.flags = so.flags; s.south.plane = so.plane; s.south.rows = so.rows;
+      s.north.buf[0] = no.buf[0]; s.north.buf[1] = no.buf[1]; s.north.flags = no.flags; s.north.plane = no.plane; s.north.rows = no.rows;
+    }
+  }
+  rc = finish_create(h);
+  if (rc) { lbm_b200_destroy(h); return rc; }
+  *handle = h;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                         int rank, int n_ranks, float density, float accel, float omega,
+                         float free_cells_inv, const int* obstacles_slab, int device)
+{
+  int rc = check_common(nx, ny_global, omega, obstacles_slab, handle);
+  if (rc) return rc;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LBM_B200_ERR_ARG, "bad rank %d of %d", rank, n_ranks);
+  if (rows < 3 || first_row < 0 || first_row + rows > ny_global) return fail(LBM_B200_ERR_ARG, "bad slab rows [%d, %d) of %d (at least 3 rows)", first_row, first_row + rows, ny_global);
+  if (n_ranks == 1 && rows != ny_global) return fail(LBM_B200_ERR_ARG, "a single rank must own the whole grid");
+  int ndev = 0;
+  cudaGetDeviceCount(&ndev);
+  if (device < 0 || device >= ndev) return fail(LBM_B200_ERR_ARG, "device %d requested but %d device(s) are visible", device, ndev);
+
+  lbm_b200* h = new lbm_b200();
+  init_common(h, nx, ny_global, density, accel, omega, free_cells_inv);
+  h->n_ranks = n_ranks;
+  h->rank0 = rank;
+  h->multi_process = n_ranks > 1;
+  h->connected = n_ranks == 1;
+  h->slabs.resize(1);
+  Slab& s = h->slabs[0];
+  s.device = device; s.rows = rows; s.first_row = first_row;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    lbm_b200_destroy(h);
+    return fail(LBM_B200_ERR_CUDA, "cannot create a stream on device %d", device);
+  }
+  s.own_stream = true;
+  rc = alloc_slab(h, s, obstacles_slab);
+  if (!rc) rc = finish_create(h);
+  if (rc) { lbm_b200_destroy(h); return rc; }
+  *handle = h;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_ipc_blob_bytes(void) { return (int)sizeof(IpcBlob); }
+
+int lbm_b200_ipc_export(lbm_b200* h, void* blob)
+{
+  if (!h || !blob) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (h->slabs.size() != 1) return fail(LBM_B200_ERR_STATE, "ipc export is for slab handles");
+  Slab& s = h->slabs[0];
+  IpcBlob b{};
+  CUDA_TRY(cudaSetDevice(s.device));
+  CUDA_TRY(cudaIpcGetMemHandle(&b.buf[0], s.buf[0]));
+  CUDA_TRY(cudaIpcGetMemHandle(&b.buf[1], s.buf[1]));
+  CUDA_TRY(cudaIpcGetMemHandle(&b.flags, s.flags));
+  b.plane = s.plane; b.rows = s.rows; b.device = s.device; b.pid = (int)getpid();
+  memcpy(blob, &b, sizeof b);
+  return LBM_B200_OK;
+}
+
+static int open_neighbour(Neighbour& n, const IpcBlob& b)
+{
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+  CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
+  n.plane = (size_t)b.plane; n.rows = b.rows; n.ipc = true;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_ipc_connect(lbm_b200* h, const void* south_blob, const void* north_blob)
+{
+  if (!h || !south_blob || !north_blob) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (!h->multi_process) return fail(LBM_B200_ERR_STATE, "ipc connect is for slab handles with more than one rank");
+  if (h->connected) return fail(LBM_B200_ERR_STATE, "already connected");
+  Slab& s = h->slabs[0];
+  IpcBlob sb, nb;
+  memcpy(&sb, south_blob, sizeof sb);
+  memcpy(&nb, north_blob, sizeof nb);
+  CUDA_TRY(cudaSetDevice(s.device));
+  int rc = open_neighbour(s.south, sb);
+  if (rc) return rc;
+  if (memcmp(&sb, &nb, sizeof sb) == 0) {           // two ranks: both neighbours are the same slab
+    s.north = s.south;
+    s.north.ipc = false;
+  } else {
+    rc = open_neighbour(s.north, nb);
+    if (rc) return rc;
+  }
+  h->connected = true;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_enqueue(lbm_b200* h, int iters)
+{
+  if (!h) return fail(LBM_B200_ERR_ARG, "NULL handle");
+  if (iters < 0) return fail(LBM_B200_ERR_ARG, "iters must be >= 0");
+  if (!h->connected) return fail(LBM_B200_ERR_STATE, "slab handle is not connected to its neighbours (lbm_b200_ipc_connect)");
+  h->last_iters = iters;
+  h->launches = 0;
+  for (Slab& s : h->slabs) {
+    int rc = ensure_av_capacity(s, (size_t)iters);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaMemsetAsync(s.cursor, 0, sizeof(unsigned), s.stream));
+  }
+  int glen = (int)h->opt_graph_steps;
+  if (glen > 0) {
+    glen = std::min(glen, kChunkSteps) & ~1;         // even, so a replay preserves the buffer parity
+    if (glen >= 2 && h->graph_len != glen) {
+      const long before = h->launches;
+      int rc = build_graphs(h, glen);
+      if (rc) return rc;
+      h->launches = before;                          // captured, not launched
+    }
+  }
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaEventRecord(s.ev_start, s.stream));
+  }
+  if (iters > 0) {
+    // the first step's body force (d2q9-bgk.c:345-348); later ones are folded into the stores
+    for (Slab& s : h->slabs) {
+      if (s.accel_row < 0) continue;
+      CUDA_TRY(cudaSetDevice(s.device));
+      lbm::accelerate_row<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
+          s.buf[h->cur], s.plane, s.mask + (size_t)(s.accel_row - 1) * h->mask_row_words, h->nx,
+          (size_t)s.accel_row * h->nx, h->sc.aw1, h->sc.aw2);
+      CUDA_TRY(cudaGetLastError());
+      h->launches++;
+    }
+    int t = 0;
+    if (glen >= 2 && h->graph_len == glen) {
+      Slab& s = h->slabs[0];
+      while (iters - 1 - t >= glen) {                // the very last step never folds a force in
+        CUDA_TRY(cudaGraphLaunch(s.graphs[h->cur], s.stream));
+        h->launches += glen + 2;
+        t += glen;
+      }
+    }
+    while (t < iters) {
+      const int n = std::min(kChunkSteps, iters - t);
+      for (int i = 0; i < n; i++) {
+        int rc = enqueue_step(h, i, t + i != iters - 1);
+        if (rc) return rc;
+      }
+      int rc = enqueue_reduce(h, n);
+      if (rc) return rc;
+      t += n;
+    }
+  }
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaEventRecord(s.ev_stop, s.stream));
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_sync(lbm_b200* h)
+{
+  if (!h) return fail(LBM_B200_ERR_ARG, "NULL handle");
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_elapsed_ms(lbm_b200* h, float* ms)
+{
+  if (!h || !ms) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  float worst = 0.f;
+  for (Slab& s : h->slabs) {
+    float t = 0.f;
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaEventElapsedTime(&t, s.ev_start, s.ev_stop));
+    worst = std::max(worst, t);
+  }
+  *ms = worst;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_fetch_av_vels(lbm_b200* h, int iters, float* av_vels)
+{
+  if (!h || (!av_vels && iters > 0)) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (iters < 0 || iters > h->last_iters) return fail(LBM_B200_ERR_ARG, "iters exceeds the last enqueue");
+  if (iters == 0) return LBM_B200_OK;
+  std::vector<float> part;
+  for (size_t i = 0; i < h->slabs.size(); i++) {
+    Slab& s = h->slabs[i];
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (i == 0) {
+      CUDA_TRY(cudaMemcpy(av_vels, s.av_dev, (size_t)iters * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {                                         // rank-order float sum, as MPI_Reduce (396)
+      part.resize(iters);
+      CUDA_TRY(cudaMemcpy(part.data(), s.av_dev, (size_t)iters * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int t = 0; t < iters; t++) av_vels[t] += part[t];
+    }
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_run(lbm_b200* h, int iters, float* av_vels)
+{
+  int rc = lbm_b200_enqueue(h, iters);
+  if (rc) return rc;
+  rc = lbm_b200_sync(h);
+  if (rc) return rc;
+  if (av_vels) return lbm_b200_fetch_av_vels(h, iters, av_vels);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_shape(const lbm_b200* h, int* nx, int* rows, int* first_row)
+{
+  if (!h) return fail(LBM_B200_ERR_ARG, "NULL handle");
+  int total = 0;
+  for (const Slab& s : h->slabs) total += s.rows;
+  if (nx) *nx = h->nx;
+  if (rows) *rows = total;
+  if (first_row) *first_row = h->slabs[0].first_row;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_get_cells(lbm_b200* h, float* cells)
+{
+  if (!h || !cells) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  size_t done = 0;
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const size_t ncell = (size_t)s.rows * h->nx;
+    float* scratch = s.buf[h->cur ^ 1];
+    const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
+    lbm::soa_to_aos<<<blocks, 256, 0, s.stream>>>(s.buf[h->cur], s.plane, (size_t)h->nx, ncell, scratch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cells + done * 9, scratch, ncell * 9 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    done += ncell;
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_cells(lbm_b200* h, const float* cells)
+{
+  if (!h || !cells) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (h->multi_process) return fail(LBM_B200_ERR_STATE, "set_cells is not available on multi-process slab handles");
+  const size_t row_floats = (size_t)h->nx * 9;
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    float* scratch = s.buf[h->cur ^ 1];
+    // owned rows plus both halo rows, taken from the periodic global grid
+    for (int r = 0; r < s.rows + 2; r++) {
+      const int gy = ((s.first_row + r - 1) % h->ny + h->ny) % h->ny;
+      CUDA_TRY(cudaMemcpyAsync(scratch + (size_t)r * row_floats, cells + (size_t)gy * row_floats,
+                               row_floats * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    }
+    const size_t ncell = (size_t)(s.rows + 2) * h->nx;
+    const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
+    lbm::aos_to_soa<<<blocks, 256, 0, s.stream>>>(scratch, s.plane, 0, ncell, s.buf[h->cur]);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_get_final_state(lbm_b200* h, float* u_x, float* u_y, float* u, float* pressure)
+{
+  if (!h) return fail(LBM_B200_ERR_ARG, "NULL handle");
+  float* outs[4] = {u_x, u_y, u, pressure};
+  size_t done = 0;
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const size_t ncell = (size_t)s.rows * h->nx;
+    float* scratch = s.buf[h->cur ^ 1];
+    const unsigned blocks = (unsigned)((ncell + 255) / 256);
+    lbm::final_state<<<blocks, 256, 0, s.stream>>>(s.buf[h->cur], s.plane, (size_t)h->nx, s.mask, h->mask_row_words,
+                                                  h->nx, ncell, h->density, scratch);
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < 4; k++)
+      if (outs[k])
+        CUDA_TRY(cudaMemcpyAsync(outs[k] + done, scratch + (size_t)k * ncell, ncell * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    done += ncell;
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
+{
+  if (!h || !key) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (!strcmp(key, "kernel")) {
+    if (value < 0 || value > 2) return fail(LBM_B200_ERR_ARG, "kernel must be 0, 1 or 2");
+    if (value == 2 && !(h->nx % 4 == 0 && h->nx >= 8)) return fail(LBM_B200_ERR_ARG, "kernel 2 needs nx %% 4 == 0 and nx >= 8");
+    h->opt_kernel = value;
+  } else if (!strcmp(key, "graph_steps")) {
+    if (value < 0) return fail(LBM_B200_ERR_ARG, "graph_steps must be >= 0");
+    h->opt_graph_steps = value;
+  } else if (!strcmp(key, "ctas_per_sm")) {
+    if (value < 0 || value > 32) return fail(LBM_B200_ERR_ARG, "ctas_per_sm must be 0..32");
+    h->opt_ctas_per_sm = value;
+  } else if (!strcmp(key, "min_ctas")) {
+    if (value != 2 && value != 3) return fail(LBM_B200_ERR_ARG, "min_ctas must be 2 or 3");
+    h->opt_min_ctas = value;
+  } else {
+    return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);
+  }
+  lbm_b200_sync(h);
+  destroy_graphs(h);
+  plan(h);
+  return ensure_partials(h);
+}
+
+int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
+{
+  if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (!strcmp(key, "kernel")) *value = use_vec4(h) ? 2 : 1;
+  else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;
+  else if (!strcmp(key, "ctas_per_sm")) *value = h->opt_ctas_per_sm;
+  else if (!strcmp(key, "min_ctas")) *value = h->opt_min_ctas;
+  else if (!strcmp(key, "grid")) *value = h->slabs[0].per_step;
+  else if (!strcmp(key, "threads")) *value = h->n_ranks == 1 ? h->slabs[0].threads_full : h->slabs[0].threads_int;
+  else if (!strcmp(key, "launches_per_step")) *value = h->n_ranks == 1 ? 1 : 2;
+  else if (!strcmp(key, "launches")) *value = h->launches;
+  else return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);
+  return LBM_B200_OK;
+}
+
+void lbm_b200_destroy(lbm_b200* h)
+{
+  if (!h) return;
+  destroy_graphs(h);
+  for (Slab& s : h->slabs) {
+    cudaSetDevice(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (Neighbour* n : {&s.south, &s.north}) {
+      if (!n->ipc) continue;
+      for (int i = 0; i < 2; i++)
+        if (n->buf[i]) cudaIpcCloseMemHandle(n->buf[i]);
+      if (n->flags) cudaIpcCloseMemHandle(n->flags);
+    }
+    for (int b = 0; b < 2; b++)
+      if (s.buf[b]) cudaFree(s.buf[b]);
+    if (s.mask) cudaFree(s.mask);
+    if (s.flags) cudaFree(s.flags);
+    if (s.partials) cudaFree(s.partials);
+    if (s.av_dev) cudaFree(s.av_dev);
+    if (s.cursor) cudaFree(s.cursor);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+    if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaGetLastError();
+  delete h;
+}
+
+}  // extern "C"

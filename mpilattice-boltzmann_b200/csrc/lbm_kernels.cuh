@@ -1,0 +1,391 @@
+// lbm_kernels.cuh -- the fused timestep kernels (sm_100a) and their small helpers.
+//
+// One timestep = ONE pass over the slab: pull-stream (propagate), bounce-back (rebound), BGK
+// collision, next step's accelerate_flow on row ny-2, and the block-level partial of
+// Sigma |m|/rho -- replacing reference d2q9-bgk.c:345-367.  Populations are nine fp32 planes
+// (structure of arrays) of (rows+2) x nx floats: padded row 0 and rows+1 are halo rows, rows
+// 1..rows are owned.  The obstacle map is 1 bit per cell, 32 cells per word, rows padded to
+// whole words.  Algorithmic traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "lbm_cell.cuh"
+
+namespace lbm {
+
+constexpr int kSegCells = 128;   // cells per warp work item in the vec4 kernel (32 lanes x 4)
+
+// What a step kernel needs.  Passed by value (lives in the constant bank).
+struct StepArgs {
+  const float* src;          // plane 0 of the source buffer
+  float* dst;                // plane 0 of the destination buffer
+  size_t plane;              // floats between planes = (rows+2)*nx
+  const uint32_t* mask;      // bit-packed obstacles of the owned rows, row r at (r-1)*mask_row_words
+  int mask_row_words;
+  int nx;
+  int chunks;                // ceil(nx / kSegCells)
+  int row_begin, row_count, row_stride;   // processed padded rows: row_begin + i*row_stride
+  int row_first, row_last;   // first / last owned padded row (1, rows)
+  int south_of_first;        // padded source row below row_first (0 = halo, or rows = y-wrap)
+  int north_of_last;         // padded source row above row_last (rows+1 = halo, or 1 = y-wrap)
+  int accel_row;             // padded row of global row ny-2 if the next step's force is to be folded in, else -1
+  StepConst c;
+  double* partials;          // one double per CTA: this launch's share of Sigma |m|/rho
+  // ---- halo exchange over peer memory (used only by the <PEER> instantiations) ----
+  float* north_dst; size_t north_plane; int north_row;   // planes 2,5,6 of row_last  -> neighbour row north_row
+  float* south_dst; size_t south_plane; int south_row;   // planes 4,7,8 of row_first -> neighbour row south_row
+  const unsigned* wait_from_south; const unsigned* wait_from_north;   // local flag words the neighbours write
+  unsigned* signal_north; unsigned* signal_south;                     // the neighbours' flag words (peer memory)
+  unsigned* epoch;           // local: number of states this slab has published
+  unsigned* done;            // local: CTA completion counter of this launch
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Blocks until both ring neighbours have published the halo rows of the state this slab is
+// about to read (their flag >= this slab's epoch).  Replaces MPI_Waitall (d2q9-bgk.c:364).
+__device__ __forceinline__ void peer_wait(const StepArgs& a)
+{
+  if (threadIdx.x == 0) {
+    const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
+    while ((int)(ld_acquire_sys(a.wait_from_south) - need) < 0) __nanosleep(20);
+    while ((int)(ld_acquire_sys(a.wait_from_north) - need) < 0) __nanosleep(20);
+  }
+  __syncthreads();
+}
+
+// After every CTA has stored its share of the outgoing halo rows into the neighbours'
+// buffers, the last CTA to finish publishes the new epoch to both neighbours.  Replaces the
+// completion of MPI_Startall's sends (d2q9-bgk.c:327).
+__device__ __forceinline__ void peer_signal(const StepArgs& a)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done = 0;
+      __threadfence_system();
+      const unsigned next = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
+      st_release_sys(a.signal_north, next);
+      st_release_sys(a.signal_south, next);
+      *reinterpret_cast<volatile unsigned*>(a.epoch) = next;
+    }
+  }
+}
+
+// Sum of `v` over the CTA, written by thread 0 to *out.  Deterministic (fixed tree).
+__device__ __forceinline__ void block_sum_to(double v, double* out)
+{
+  __shared__ double warp_sums[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nwarps = (blockDim.x + 31) >> 5;
+    double s = (lane < nwarps) ? warp_sums[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) *out = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 2 ("vec4"): one warp per 128-cell row segment, four cells per lane.  Every global
+// access is a 128-bit aligned, fully coalesced row load/store; the +-1 x-shifts of the six
+// x-moving populations come from the neighbouring lane by warp shuffle, and only the two end
+// lanes of a segment fetch one extra scalar across the segment (or the periodic) boundary.
+// Persistent grid: CTAs stride over the segments.  Requires nx % 4 == 0, nx >= 8.
+// ---------------------------------------------------------------------------------------
+template <bool PEER, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
+{
+  if (PEER) peer_wait(a);
+
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const long nseg = (long)a.row_count * a.chunks;
+  const float* __restrict__ src = a.src;
+  float* __restrict__ dst = a.dst;
+  const size_t P = a.plane;
+  double acc = 0.0;
+
+  for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
+    const int ri = (int)(seg / a.chunks);
+    const int ch = (int)(seg - (long)ri * a.chunks);
+    const int row = a.row_begin + ri * a.row_stride;
+    const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
+    const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
+    const int x0 = ch * kSegCells + lane * 4;
+    const bool active = x0 < a.nx;
+    const bool west_edge = (lane == 0);
+    const bool east_edge = (lane == 31) || (x0 + 4 >= a.nx);
+    const int xw = (x0 == 0) ? a.nx - 1 : x0 - 1;
+    const int xe = (x0 + 4 >= a.nx) ? 0 : x0 + 4;
+
+    const size_t o_c = (size_t)row * a.nx, o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
+
+    float4 c[9];
+    float e_c = 0.f, e_s = 0.f, e_n = 0.f;
+    uint32_t mw = 0;
+    if (active) {
+      c[0] = __ldg(reinterpret_cast<const float4*>(src + 0 * P + o_c + x0));
+      c[1] = __ldg(reinterpret_cast<const float4*>(src + 1 * P + o_c + x0));
+      c[2] = __ldg(reinterpret_cast<const float4*>(src + 2 * P + o_s + x0));
+      c[3] = __ldg(reinterpret_cast<const float4*>(src + 3 * P + o_c + x0));
+      c[4] = __ldg(reinterpret_cast<const float4*>(src + 4 * P + o_n + x0));
+      c[5] = __ldg(reinterpret_cast<const float4*>(src + 5 * P + o_s + x0));
+      c[6] = __ldg(reinterpret_cast<const float4*>(src + 6 * P + o_s + x0));
+      c[7] = __ldg(reinterpret_cast<const float4*>(src + 7 * P + o_n + x0));
+      c[8] = __ldg(reinterpret_cast<const float4*>(src + 8 * P + o_n + x0));
+      mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5));
+      if (west_edge || east_edge) {
+        // west end: populations 1, 5, 8 arrive from x-1; east end: 3, 6, 7 arrive from x+1
+        e_c = __ldg(west_edge ? src + 1 * P + o_c + xw : src + 3 * P + o_c + xe);
+        e_s = __ldg(west_edge ? src + 5 * P + o_s + xw : src + 6 * P + o_s + xe);
+        e_n = __ldg(west_edge ? src + 8 * P + o_n + xw : src + 7 * P + o_n + xe);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // neighbour lanes supply the value that crosses the 4-cell boundary
+    const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+    const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+    const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+    const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+    const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+    const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+    const float w1v = west_edge ? e_c : up1, w5v = west_edge ? e_s : up5, w8v = west_edge ? e_n : up8;
+    const float e3v = east_edge ? e_c : dn3, e6v = east_edge ? e_s : dn6, e7v = east_edge ? e_n : dn7;
+
+    if (active) {
+      const unsigned bits = (mw >> (x0 & 31)) & 0xFu;
+      const bool fold_accel = (row == a.accel_row);
+      float f[4][9];
+      f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+      f[0][1] = w1v;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+      f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+      f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = e3v;
+      f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+      f[0][5] = w5v;    f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+      f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = e6v;
+      f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = e7v;
+      f[0][8] = w8v;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+
+      float u4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool blocked = (bits >> j) & 1u;
+        const float u = collide(f[j], blocked, a.c.omega);
+        u4 = (j == 0) ? u : add(u4, u);
+        if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+      }
+      acc += (double)u4;
+
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        *reinterpret_cast<float4*>(dst + k * P + o_c + x0) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+
+      if (PEER) {
+        // one-row halo exchange: NVLink stores straight into the neighbour's halo row
+        // (replaces the MPI_Send_init/MPI_Recv_init pairs of d2q9-bgk.c:295-313; only the
+        // three populations that cross the slab boundary travel, 12*nx B instead of 36*nx B)
+        if (row == a.row_last) {
+          const size_t o = (size_t)a.north_row * a.nx + x0;
+          *reinterpret_cast<float4*>(a.north_dst + 2 * a.north_plane + o) = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
+          *reinterpret_cast<float4*>(a.north_dst + 5 * a.north_plane + o) = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
+          *reinterpret_cast<float4*>(a.north_dst + 6 * a.north_plane + o) = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
+        }
+        if (row == a.row_first) {
+          const size_t o = (size_t)a.south_row * a.nx + x0;
+          *reinterpret_cast<float4*>(a.south_dst + 4 * a.south_plane + o) = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
+          *reinterpret_cast<float4*>(a.south_dst + 7 * a.south_plane + o) = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
+          *reinterpret_cast<float4*>(a.south_dst + 8 * a.south_plane + o) = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
+        }
+      }
+    }
+  }
+
+  block_sum_to(acc, a.partials + blockIdx.x);
+  if (PEER) peer_signal(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 1 ("scalar"): one cell per thread, any nx.  The generic path (nx not a multiple of
+// 4) and the baseline the vec4 kernel is measured against.
+// ---------------------------------------------------------------------------------------
+template <bool PEER>
+__global__ void __launch_bounds__(256) step_scalar(const StepArgs a)
+{
+  if (PEER) peer_wait(a);
+
+  const float* __restrict__ src = a.src;
+  float* __restrict__ dst = a.dst;
+  const size_t P = a.plane;
+  const long ncell = (long)a.row_count * a.nx;
+  double acc = 0.0;
+
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long)gridDim.x * blockDim.x) {
+    const int ri = (int)(i / a.nx);
+    const int x = (int)(i - (long)ri * a.nx);
+    const int row = a.row_begin + ri * a.row_stride;
+    const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
+    const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
+    const int xw = (x == 0) ? a.nx - 1 : x - 1;
+    const int xe = (x + 1 >= a.nx) ? 0 : x + 1;
+    const size_t o_c = (size_t)row * a.nx, o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
+
+    float f[9];
+    f[0] = __ldg(src + 0 * P + o_c + x);
+    f[1] = __ldg(src + 1 * P + o_c + xw);
+    f[2] = __ldg(src + 2 * P + o_s + x);
+    f[3] = __ldg(src + 3 * P + o_c + xe);
+    f[4] = __ldg(src + 4 * P + o_n + x);
+    f[5] = __ldg(src + 5 * P + o_s + xw);
+    f[6] = __ldg(src + 6 * P + o_s + xe);
+    f[7] = __ldg(src + 7 * P + o_n + xe);
+    f[8] = __ldg(src + 8 * P + o_n + xw);
+    const uint32_t mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x >> 5));
+    const bool blocked = (mw >> (x & 31)) & 1u;
+
+    acc += (double)collide(f, blocked, a.c.omega);
+    if (row == a.accel_row) accelerate(f, blocked, a.c.aw1, a.c.aw2);
+
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst[k * P + o_c + x] = f[k];
+
+    if (PEER) {
+      if (row == a.row_last) {
+        const size_t o = (size_t)a.north_row * a.nx + x;
+        a.north_dst[2 * a.north_plane + o] = f[2];
+        a.north_dst[5 * a.north_plane + o] = f[5];
+        a.north_dst[6 * a.north_plane + o] = f[6];
+      }
+      if (row == a.row_first) {
+        const size_t o = (size_t)a.south_row * a.nx + x;
+        a.south_dst[4 * a.south_plane + o] = f[4];
+        a.south_dst[7 * a.south_plane + o] = f[7];
+        a.south_dst[8 * a.south_plane + o] = f[8];
+      }
+    }
+  }
+
+  block_sum_to(acc, a.partials + blockIdx.x);
+  if (PEER) peer_signal(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// Small kernels around the step.
+// ---------------------------------------------------------------------------------------
+
+// accelerate_flow (d2q9-bgk.c:442-478) as a pre-pass on one row: needed once per run, before
+// the first step; all later steps get their force folded into the previous step's store.
+__global__ void accelerate_row(float* buf, size_t plane, const uint32_t* mask_row, int nx, size_t row_off,
+                               float aw1, float aw2)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nx) return;
+  const bool blocked = (mask_row[x >> 5] >> (x & 31)) & 1u;
+  float* p = buf + row_off + x;
+  const float f3 = p[3 * plane], f6 = p[6 * plane], f7 = p[7 * plane];
+  if (!blocked && sub(f3, aw1) > 0.0f && sub(f6, aw2) > 0.0f && sub(f7, aw2) > 0.0f) {
+    p[1 * plane] = add(p[1 * plane], aw1);
+    p[5 * plane] = add(p[5 * plane], aw2);
+    p[8 * plane] = add(p[8 * plane], aw2);
+    p[3 * plane] = sub(f3, aw1);
+    p[6 * plane] = sub(f6, aw2);
+    p[7 * plane] = sub(f7, aw2);
+  }
+}
+
+// av[base + t] = (float)(sum of the step's CTA partials, fixed order, fp64) * free_cells_inv
+// for t in [0, steps): d2q9-bgk.c:367.  One warp per step.  `cursor` (device) holds base and
+// is advanced by `steps` so that graph replays append.
+__global__ void reduce_partials(const double* partials, int per_step, int steps, float free_cells_inv,
+                                float* av, unsigned* cursor)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned base = *cursor;
+  if (warp < steps) {
+    const double* p = partials + (size_t)warp * per_step;
+    double s = 0.0;
+    for (int i = lane; i < per_step; i += 32) s += p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) av[base + warp] = mul((float)s, free_cells_inv);
+  }
+}
+__global__ void advance_cursor(unsigned* cursor, unsigned by) { *cursor += by; }
+
+// uniform initial state, every padded row (d2q9-bgk.c:880-902)
+__global__ void fill_planes(float* buf, size_t plane, float w0, float w1, float w2)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  buf[i] = w0;
+#pragma unroll
+  for (int k = 1; k < 5; k++) buf[k * plane + i] = w1;
+#pragma unroll
+  for (int k = 5; k < 9; k++) buf[k * plane + i] = w2;
+}
+
+// planes (padded rows [row0, row0+nrows)) -> array of structs, and back
+__global__ void soa_to_aos(const float* buf, size_t plane, size_t first, size_t ncell, float* aos)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell * 9) return;
+  const size_t cell = i / 9;
+  const int k = (int)(i - cell * 9);
+  aos[i] = buf[k * plane + first + cell];
+}
+__global__ void aos_to_soa(const float* aos, size_t plane, size_t first, size_t ncell, float* buf)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell * 9) return;
+  const size_t cell = i / 9;
+  const int k = (int)(i - cell * 9);
+  buf[k * plane + first + cell] = aos[i];
+}
+
+// Macroscopic fields exactly as write_values computes them (d2q9-bgk.c:1076-1111); out holds
+// four planes of `ncell` floats: u_x, u_y, |u|, pressure.
+__global__ void final_state(const float* buf, size_t plane, size_t first, const uint32_t* mask, int mask_row_words,
+                            int nx, size_t ncell, float density, float* out)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const size_t r = i / nx;
+  const int x = (int)(i - r * nx);
+  const bool blocked = (mask[r * mask_row_words + (x >> 5)] >> (x & 31)) & 1u;
+  constexpr float c_sq = 1.0f / 3.0f;
+  float ux = 0.f, uy = 0.f, u = 0.f, pr = mul(density, c_sq);
+  if (!blocked) {
+    float f[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k] = buf[k * plane + first + i];
+    float rho = add(0.0f, f[0]);
+#pragma unroll
+    for (int k = 1; k < 9; k++) rho = add(rho, f[k]);
+    ux = __fdiv_rn(sub(add(add(f[1], f[5]), f[8]), add(add(f[3], f[6]), f[7])), rho);
+    uy = __fdiv_rn(sub(add(add(f[2], f[5]), f[6]), add(add(f[4], f[7]), f[8])), rho);
+    u = __fsqrt_rn(add(mul(ux, ux), mul(uy, uy)));
+    pr = mul(rho, c_sq);
+  }
+  out[i] = ux; out[ncell + i] = uy; out[2 * ncell + i] = u; out[3 * ncell + i] = pr;
+}
+
+}  // namespace lbm

@@ -1,0 +1,86 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/lbm_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lbm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_b200_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/lbm_b200.h but not exported"
+    assert sorted(pkg.SIGNATURES) == names, "the ctypes binding must cover the header exactly"
+
+
+def test_no_torch_or_cxx_types_in_the_header():
+    text = open(os.path.join(ROOT, "include", "lbm_b200.h")).read()
+    assert 'extern "C"' in text
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)       # declarations only, not the prose
+    for forbidden in ("torch", "at::", "std::", "cudaStream_t", "template"):
+        assert forbidden not in text
+
+
+def test_abi_version(pkg):
+    assert pkg.library().lbm_b200_abi_version() == 1
+
+
+def test_oracle_is_not_linked_into_the_product(pkg):
+    """The product must not route through oracle/: neither the library nor the CLI references it."""
+    for path in (pkg.LIB_PATH, pkg.EXE_PATH):
+        blob = open(path, "rb").read()
+        assert b"lbm_oracle_" not in blob and b"liblbm_oracle" not in blob
+    src_dir = os.path.join(ROOT, "mpilattice-boltzmann_b200")
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for needle in ("oracle_lib", "liblbm_oracle", "lbm_oracle_", "import oracle"):
+                    assert needle not in text, f"{f} touches the oracle ({needle})"
+                assert not re.search(r"#\s*include[^\n]*oracle", text), f"{f} includes an oracle header"
+
+
+@pytest.mark.parametrize("ny,n", [(128, 1), (128, 2), (128, 8), (1024, 8), (130, 4), (131, 8), (16384, 8), (24, 8), (27, 8)])
+def test_decompose_matches_reference_rule(pkg, oracle, ny, n):
+    rows, first = pkg.decompose(ny, n)
+    ref_rows, ref_first = oracle.decompose(ny, n)     # restates d2q9-bgk.c:834-862
+    assert rows.tolist() == ref_rows.tolist()
+    assert first.tolist() == ref_first.tolist()
+    assert rows.sum() == ny and rows[-1] >= 3 or n == 1
+
+
+def test_decompose_refuses_thin_slabs(pkg):
+    with pytest.raises(pkg.LBMError, match="at least 3 rows"):
+        pkg.decompose(16, 8)          # the reference would create 1- and 2-row slabs here
+
+
+def test_free_cells_inv_counts_blocked_once(pkg):
+    ob = np.zeros((8, 8), np.int32)
+    ob[0, :] = 1
+    ob[3, 3] = 7                       # any non-zero value is a blocked cell
+    assert pkg.free_cells_inv(ob) == np.float32(1.0) / np.float32(64 - 9)
+
+
+def test_compute_fails_loudly_without_a_gpu(pkg):
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.LBMError, match="no CUDA device"):
+        pkg.Simulation(16, 16, 0.1, 0.005, 1.85, np.zeros((16, 16), np.int32))
+
+
+def test_bad_arguments_are_rejected_before_any_device_work(pkg):
+    with pytest.raises(pkg.LBMError, match="too small"):
+        pkg.Simulation(2, 2, 0.1, 0.005, 1.85, np.zeros((2, 2), np.int32))
+    with pytest.raises(ValueError):
+        pkg.Simulation(16, 16, 0.1, 0.005, 1.85, np.zeros((8, 16), np.int32))

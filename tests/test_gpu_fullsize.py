@@ -1,0 +1,57 @@
+"""BASELINE.json's full size (16384 x 16384) through size-independent properties.
+
+The oracle cannot step 268 M cells in test time, but a grid whose obstacle map is periodic in x
+with period P evolves periodically in x: every column x behaves exactly like column x mod P of
+a P-wide grid (the x-wrap joins the copies seamlessly).  So the full-size GPU run is checked
+BIT FOR BIT against the oracle on the narrow grid, tiled."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+NX = NY = 16384
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
+
+
+def narrow_pattern(period, rng):
+    ob = (rng.random((NY, period)) < 0.02).astype(np.int32)
+    ob[0, :] = ob[-1, :] = 1                     # the synthetic deck's channel walls
+    ob[NY - 2, : period // 4] = 1                # some blocked cells in the accelerated row
+    return ob
+
+
+@pytest.mark.parametrize("n_slabs", [1, 4])
+def test_full_size_matches_tiled_oracle(pkg, oracle, n_slabs):
+    period, iters = 128, 6
+    rng = np.random.default_rng(42)
+    narrow = narrow_pattern(period, rng)
+    inv_narrow = pkg.free_cells_inv(narrow)
+    cells = oracle.init_cells(period, NY, DENSITY)
+    av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, inv_narrow)
+    ref_fields = oracle.final_state(cells, narrow, DENSITY)
+
+    obstacles = np.tile(narrow, (1, NX // period))
+    with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        av = sim.run(iters)
+        fields = sim.final_state()
+        for got, want in zip(fields, ref_fields):
+            tiled = np.tile(want, (1, NX // period))
+            assert np.array_equal(bits(got), bits(tiled))
+        # same average: sum over 128 identical copies / (128 x free cells)
+        assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-5
+
+
+def test_plain_channel_is_x_invariant_and_matches_an_8_wide_oracle(pkg, oracle):
+    """The bench workload itself (walls on rows 0 and ny-1, nothing else)."""
+    iters = 8
+    narrow = pkg.decks.channel_obstacles(8, NY)
+    cells = oracle.init_cells(8, NY, DENSITY)
+    av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow))
+    ref_pressure = oracle.final_state(cells, narrow, DENSITY)[3]
+    with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, pkg.decks.channel_obstacles(NX, NY)) as sim:
+        av = sim.run(iters)
+        pressure = sim.final_state()[3]
+    assert np.array_equal(bits(pressure), bits(np.repeat(ref_pressure[:, :1], NX, axis=1)))
+    assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-5

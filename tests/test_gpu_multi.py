@@ -1,0 +1,60 @@
+"""Row slabs on SEVERAL B200s: halo rows travel as NVLink stores from the edge-row kernel,
+flag words order the exchange.  Needs >= 2 visible GPUs (gpurun --gpus 2); skipped otherwise.
+(The same code path with all slabs on one device is covered by test_gpu_parity.py.)"""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits, random_cells, random_obstacles
+
+pytestmark = pytest.mark.gpu
+
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
+
+
+def need_gpus(pkg, n):
+    if pkg.device_count() < n:
+        pytest.skip(f"needs {n} GPUs, {pkg.device_count()} visible")
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_single_process_multi_device(pkg, oracle, n):
+    need_gpus(pkg, n)
+    rng = np.random.default_rng(n)
+    nx, ny, iters = 256, 8 * n + 5, 200
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n) as sim:
+        sim.set_cells(cells0)
+        av = sim.run(iters)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-5
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, tmp_path):
+    """torchrun-style launch: n processes, CUDA IPC handles exchanged with torch.distributed."""
+    need_gpus(pkg, n)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "result.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    data = np.load(out)
+    obstacles, cells = data["obstacles"], data["cells"]
+    iters = int(data["iters"])
+    ny, nx = obstacles.shape
+    ref = oracle.init_cells(nx, ny, DENSITY)
+    ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    assert np.array_equal(bits(cells), bits(ref))
+    assert np.max(np.abs(data["av"] - ref_av) / ref_av) < 1e-5

@@ -1,0 +1,182 @@
+"""GPU parity proper: the CUDA path (through the C-ABI) against the oracle on the same inputs.
+
+Bar: every population of every cell BIT-EXACT (the kernels issue the reference's fp32
+operations in the reference's order, no FMA contraction); av_vels to 1e-5 relative (the device
+sums |m|/rho in a fixed tree in fp64, the reference sequentially in fp32 -- summation order
+is the only difference)."""
+import numpy as np
+import pytest
+
+from conftest import bits, random_cells, random_obstacles
+
+pytestmark = pytest.mark.gpu
+
+AV_RTOL = 1e-5
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
+
+
+def oracle_run(oracle, pkg, cells0, obstacles, iters, density=DENSITY, accel=ACCEL, omega=OMEGA):
+    cells = cells0.copy()
+    av = oracle.run(cells, obstacles, iters, density, accel, omega, pkg.free_cells_inv(obstacles))
+    return cells, av
+
+
+def assert_parity(sim, oracle, pkg, cells0, obstacles, iters, **kw):
+    ref_cells, ref_av = oracle_run(oracle, pkg, cells0, obstacles, iters, **kw)
+    av = sim.run(iters)
+    got = sim.get_cells()
+    mism = np.argwhere(bits(got) != bits(ref_cells))
+    assert mism.size == 0, f"{len(mism)} populations differ, first at (y,x,k)={mism[0].tolist()}"
+    if iters:
+        assert np.max(np.abs(av.astype(np.float64) - ref_av) / np.abs(ref_av)) < AV_RTOL
+    return ref_cells
+
+
+# nx: multiples of 128, ragged segments (136, 200), tiny (8, 12), and not a multiple of 4 (scalar kernel)
+SHAPES = [(128, 128), (256, 64), (136, 20), (200, 33), (8, 8), (12, 5), (1024, 16), (30, 17), (7, 9), (129, 12)]
+
+
+@pytest.mark.parametrize("nx,ny", SHAPES)
+def test_uniform_start_bit_exact(pkg, oracle, nx, ny):
+    rng = np.random.default_rng(nx * 131 + ny)
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        assert sim.get_option("kernel") == (2 if nx % 4 == 0 and nx >= 8 else 1)
+        cells0 = oracle.init_cells(nx, ny, DENSITY)
+        assert np.array_equal(bits(sim.get_cells()), bits(cells0))     # initialise(): d2q9-bgk.c:880-902
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 30)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("nx,ny,walls", [(128, 24, True), (136, 19, False), (256, 7, False)])
+def test_random_state_bit_exact(pkg, oracle, kernel, nx, ny, walls):
+    """Arbitrary positive states, obstacles on every edge, open top/bottom rows (y-wrap), x-wrap."""
+    rng = np.random.default_rng(kernel * 7 + nx + ny)
+    obstacles = random_obstacles(rng, ny, nx, 0.10, walls=walls)
+    obstacles[:, 0] = rng.random(ny) < 0.5                 # ragged side walls: x-wrap sees fluid and solid
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("kernel", kernel)
+        sim.set_cells(cells0)
+        assert np.array_equal(bits(sim.get_cells()), bits(cells0))
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 17)
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 3])
+def test_short_runs_and_the_folded_accelerate(pkg, oracle, iters):
+    """accelerate_flow is folded into the previous step's store; 0/1/2/3 steps pin the pre-pass,
+    the fold and the un-accelerated last step."""
+    rng = np.random.default_rng(5)
+    nx, ny = 128, 12
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    obstacles[ny - 2, 10:20] = 1                            # blocked cells inside the accelerated row
+    cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, 30:40, 3] = 1e-5                         # cells where the force must NOT be applied (f3 - w1 <= 0)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+
+
+def test_runs_compose(pkg, oracle):
+    """run(7) + run(6) + run(0) + run(1) == run(14): the handle keeps the canonical state between runs."""
+    rng = np.random.default_rng(9)
+    nx, ny = 256, 20
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    ref_cells, ref_av = oracle_run(oracle, pkg, cells0, obstacles, 14)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(7), sim.run(6), sim.run(0), sim.run(1)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
+        assert np.max(np.abs(av - ref_av) / ref_av) < AV_RTOL
+
+
+@pytest.mark.parametrize("min_ctas,ctas_per_sm", [(2, 0), (3, 0), (2, 1)])
+def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per_sm):
+    rng = np.random.default_rng(11)
+    nx, ny = 1024, 40
+    obstacles = random_obstacles(rng, ny, nx, 0.03)
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("min_ctas", min_ctas)
+        sim.set_option("ctas_per_sm", ctas_per_sm)
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 9)
+
+
+@pytest.mark.parametrize("graph_steps,iters", [(4, 23), (8, 8), (6, 5), (16, 300)])
+def test_cuda_graph_replay_is_identical(pkg, oracle, graph_steps, iters):
+    rng = np.random.default_rng(13)
+    nx, ny = 128, 16
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("graph_steps", graph_steps)
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+
+
+def test_av_vels_is_deterministic(pkg):
+    rng = np.random.default_rng(17)
+    nx, ny = 512, 64
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    runs = []
+    for _ in range(2):
+        with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+            runs.append(sim.run(50))
+    assert np.array_equal(bits(runs[0]), bits(runs[1]))
+
+
+@pytest.mark.parametrize("n_slabs,nx,ny", [(2, 128, 16), (3, 136, 19), (4, 256, 31), (8, 128, 24)])
+def test_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny):
+    """The multi-GPU path (edge/interior launches, halo rows stored into the neighbour's buffer,
+    flag words) with all slabs on device 0 in one stream: same bits as the single domain."""
+    rng = np.random.default_rng(n_slabs * 100 + ny)
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        assert sim.get_option("launches_per_step") == 2
+        sim.set_cells(cells0)
+        ref = assert_parity(sim, oracle, pkg, cells0, obstacles, 21)
+        ux, uy, u, pr = sim.final_state()
+        rux, ruy, ru, rpr = oracle.final_state(ref, obstacles, DENSITY)
+        for got, want in ((ux, rux), (uy, ruy), (u, ru), (pr, rpr)):
+            assert np.array_equal(bits(got), bits(want))
+
+
+def test_final_state_fields_bit_exact(pkg, oracle):
+    rng = np.random.default_rng(19)
+    nx, ny = 200, 33
+    obstacles = random_obstacles(rng, ny, nx, 0.1)
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_cells(cells0)
+        sim.run(5)
+        fields = sim.final_state()
+        ref = oracle.final_state(sim.get_cells(), obstacles, DENSITY)
+    for got, want in zip(fields, ref):
+        assert np.array_equal(bits(got), bits(want))
+    assert np.all(fields[3][obstacles == 1] == np.float32(DENSITY) * (np.float32(1.0) / np.float32(3.0)))
+    assert np.all(fields[2][obstacles == 1] == 0)
+
+
+def test_other_physical_parameters(pkg, oracle):
+    rng = np.random.default_rng(23)
+    nx, ny = 128, 20
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx, density=0.3)
+    with pkg.Simulation(nx, ny, 0.3, 0.01, 1.2, obstacles) as sim:
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 11, density=0.3, accel=0.01, omega=1.2)
+
+
+def test_total_density_is_conserved_on_device(pkg, oracle):
+    rng = np.random.default_rng(29)
+    nx, ny = 256, 64
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        before = oracle.total_density(sim.get_cells())
+        sim.run(400)
+        after = oracle.total_density(sim.get_cells())
+    assert abs(after - before) / before < 1e-5

@@ -1,0 +1,47 @@
+"""world_size-2 (and 3) gloo runs of the row-slab path on CPU: slabs + 3-plane halo exchange
+reproduce the single-domain oracle bit for bit (final_state is decomposition-invariant;
+av_vels agrees to summation-order noise)."""
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import random_cells, random_obstacles
+
+import slab_ring
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("size,nx,ny", [(2, 32, 24), (2, 40, 17), (3, 16, 19)])
+def test_slab_ring_matches_single_domain(pkg, oracle, size, nx, ny):
+    rng = np.random.default_rng(size * 1000 + ny)
+    iters, density, accel, omega = 25, 0.1, 0.005, 1.85
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))   # odd ny: open top/bottom, y-wrap in play
+    cells0 = random_cells(rng, ny, nx, density)
+    inv = pkg.free_cells_inv(obstacles)
+
+    whole = cells0.copy()
+    av_whole = oracle.run(whole, obstacles, iters, density, accel, omega, inv)
+
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = free_port()
+    args = (nx, ny, iters, density, accel, omega, obstacles, cells0)
+    procs = [ctx.Process(target=slab_ring.worker, args=(r, size, port, args, queue)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=300) for _ in range(size)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    results.sort(key=lambda r: r[0])
+    stitched = np.concatenate([r[1] for r in results], axis=0)
+    assert np.array_equal(stitched.view(np.uint32), whole.view(np.uint32)), "slab run differs from the single domain"
+    av = results[0][2]
+    assert np.max(np.abs(av - av_whole) / np.abs(av_whole)) < 1e-5
