@@ -323,7 +323,7 @@ def bench_ours(args, pkg):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = cells_global * timesteps / e2e_s / 1e6
-    pressure_ok = bool(np.isfinite(fields_t[3]).all())
+    pressure_ok = bool(torch.isfinite(fields_t[3]).all())
     sim.close()
     if not pressure_ok:
         sys.exit("bench.py: e2e run produced a non-finite pressure field")

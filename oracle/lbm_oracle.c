@@ -134,6 +134,8 @@ static inline double oracle_cell(const float* cells, float* tmp_cells, int block
  * are updated in parallel; the Sigma|u| accumulation is then replayed strictly in the
  * reference's sequential order (row-major, float accumulator through a double add) so the
  * result does not depend on the thread count. */
+static double oracle_exact_sum;   /* fp64 sum of the last lbm_oracle_timestep_rows call (test aid) */
+
 float lbm_oracle_timestep_rows(const float* cells, float* tmp_cells, const int* obstacles,
                                int nx, int start, int end, float omega, double* scratch)
 {
@@ -146,9 +148,14 @@ float lbm_oracle_timestep_rows(const float* cells, float* tmp_cells, const int* 
     }
   }
   float tot_u = 0.0f;                                              /* 502 */
+  double exact = 0.0;
   long n = (long)(end - start) * nx;
   for (long c = 0; c < n; c++)
-    if (scratch[c] >= 0.0) tot_u += scratch[c];                    /* 667: float += double */
+    if (scratch[c] >= 0.0) {
+      tot_u += scratch[c];                                         /* 667: float += double */
+      exact += scratch[c];
+    }
+  oracle_exact_sum = exact;
   return tot_u;
 }
 
@@ -156,9 +163,13 @@ float lbm_oracle_timestep_rows(const float* cells, float* tmp_cells, const int* 
  * wrap (295-303: halo above the last row <- first row, halo below the first row <- last
  * row), then accelerate (345-348), interior rows (350), the two edge rows (365-366), the
  * per-step average (367) and the buffer swap (376-378).
- * cells: ny*nx*9 floats (no halo), updated in place.  av_vels: iters floats. */
+ * cells: ny*nx*9 floats (no halo), updated in place.  av_vels: iters floats.
+ * av_exact (optional): the same per-cell terms summed in fp64 -- NOT what the reference
+ * computes; it separates "the GPU's terms are right" from "the reference's sequential fp32
+ * accumulation has rounding error of its own" in the av_vels comparison. */
 int lbm_oracle_run(int nx, int ny, int iters, float density, float accel, float omega,
-                   float free_cells_inv, const int* obstacles, float* cells, float* av_vels)
+                   float free_cells_inv, const int* obstacles, float* cells, float* av_vels,
+                   double* av_exact)
 {
   long row = (long)nx * NSPEEDS;
   float* a = (float*)malloc(sizeof(float) * row * (ny + 2));
@@ -176,9 +187,13 @@ int lbm_oracle_run(int nx, int ny, int iters, float density, float accel, float 
     lbm_oracle_accelerate_row(a + row * (ny - 1), obst + (long)nx * (ny - 1), nx,
                               density, accel);                     /* 449: ii = ny_local-1 */
     float local = lbm_oracle_timestep_rows(a, b, obst, nx, 2, ny, omega, scratch);      /* 350 */
+    double exact = oracle_exact_sum;
     local += lbm_oracle_timestep_rows(a, b, obst, nx, 1, 2, omega, scratch);            /* 365 */
+    exact += oracle_exact_sum;
     local += lbm_oracle_timestep_rows(a, b, obst, nx, ny, ny + 1, omega, scratch);      /* 366 */
+    exact += oracle_exact_sum;
     av_vels[tt] = local * free_cells_inv;                          /* 367 */
+    if (av_exact) av_exact[tt] = exact * (double)free_cells_inv;
     float* t = a; a = b; b = t;                                    /* 376-378 */
   }
   memcpy(cells, a + row, sizeof(float) * row * ny);

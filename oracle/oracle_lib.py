@@ -43,7 +43,7 @@ def lib():
                                                ctypes.c_float, _f64p]
         L.lbm_oracle_timestep_rows.restype = ctypes.c_float
         L.lbm_oracle_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
-                                     ctypes.c_float, ctypes.c_float, _i32p, _f32p, _f32p]
+                                     ctypes.c_float, ctypes.c_float, _i32p, _f32p, _f32p, ctypes.c_void_p]
         L.lbm_oracle_run.restype = ctypes.c_int
         L.lbm_oracle_av_velocity.argtypes = [_f32p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_float]
         L.lbm_oracle_av_velocity.restype = ctypes.c_float
@@ -73,16 +73,20 @@ def init_cells(nx: int, ny: int, density: float) -> np.ndarray:
 
 
 def run(cells: np.ndarray, obstacles: np.ndarray, iters: int, density: float, accel: float, omega: float,
-        free_cells_inv: float):
-    """Advances `cells` ([ny, nx, 9] float32, in place) by `iters` steps; returns av_vels float32[iters]."""
+        free_cells_inv: float, exact: bool = False):
+    """Advances `cells` ([ny, nx, 9] float32, in place) by `iters` steps; returns av_vels float32[iters]
+    (the reference's sequential fp32 accumulation).  With exact=True also returns float64[iters]: the same
+    per-cell terms summed in fp64."""
     ny, nx = obstacles.shape
     assert cells.shape == (ny, nx, 9) and cells.dtype == np.float32 and cells.flags.c_contiguous
     av = np.zeros(max(iters, 1), np.float32)
+    av_exact = np.zeros(max(iters, 1), np.float64) if exact else None
     rc = lib().lbm_oracle_run(nx, ny, iters, density, accel, omega, free_cells_inv,
-                              np.ascontiguousarray(obstacles, np.int32), cells, av)
+                              np.ascontiguousarray(obstacles, np.int32), cells, av,
+                              av_exact.ctypes.data if exact else None)
     if rc != 0:
         raise MemoryError("oracle allocation failed")
-    return av[:iters]
+    return (av[:iters], av_exact[:iters]) if exact else av[:iters]
 
 
 def slab_timestep(cells: np.ndarray, tmp_cells: np.ndarray, obstacles: np.ndarray, start: int, end: int,

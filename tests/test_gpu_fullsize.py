@@ -40,7 +40,7 @@ def test_full_size_matches_tiled_oracle(pkg, oracle, n_slabs):
             tiled = np.tile(want, (1, NX // period))
             assert np.array_equal(bits(got), bits(tiled))
         # same average: sum over 128 identical copies / (128 x free cells)
-        assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-5
+        assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-4
 
 
 def test_plain_channel_is_x_invariant_and_matches_an_8_wide_oracle(pkg, oracle):
@@ -54,4 +54,4 @@ def test_plain_channel_is_x_invariant_and_matches_an_8_wide_oracle(pkg, oracle):
         av = sim.run(iters)
         pressure = sim.final_state()[3]
     assert np.array_equal(bits(pressure), bits(np.repeat(ref_pressure[:, :1], NX, axis=1)))
-    assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-5
+    assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 1e-4

@@ -1,9 +1,11 @@
 """GPU parity proper: the CUDA path (through the C-ABI) against the oracle on the same inputs.
 
 Bar: every population of every cell BIT-EXACT (the kernels issue the reference's fp32
-operations in the reference's order, no FMA contraction); av_vels to 1e-5 relative (the device
-sums |m|/rho in a fixed tree in fp64, the reference sequentially in fp32 -- summation order
-is the only difference)."""
+operations in the reference's order, no FMA contraction).  av_vels: the device sums the
+per-cell |m|/rho terms in a fixed fp64 tree, the reference sequentially in an fp32 accumulator,
+so summation order is the only difference; tolerances: 2e-6 relative against the oracle's
+fp64 sum of the same terms (AV_RTOL_EXACT), 1e-4 against the reference-order fp32 sum
+(AV_RTOL_REF, the reference's own accumulation error at these sizes)."""
 import numpy as np
 import pytest
 
@@ -11,24 +13,30 @@ from conftest import bits, random_cells, random_obstacles
 
 pytestmark = pytest.mark.gpu
 
-AV_RTOL = 1e-5
+AV_RTOL_EXACT = 2e-6
+AV_RTOL_REF = 1e-4
 DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
 
 
 def oracle_run(oracle, pkg, cells0, obstacles, iters, density=DENSITY, accel=ACCEL, omega=OMEGA):
     cells = cells0.copy()
-    av = oracle.run(cells, obstacles, iters, density, accel, omega, pkg.free_cells_inv(obstacles))
-    return cells, av
+    av, av_exact = oracle.run(cells, obstacles, iters, density, accel, omega, pkg.free_cells_inv(obstacles), exact=True)
+    return cells, av, av_exact
+
+
+def assert_av(av, ref_av, ref_exact):
+    if len(av):
+        assert np.max(np.abs(av.astype(np.float64) - ref_exact) / np.abs(ref_exact)) < AV_RTOL_EXACT
+        assert np.max(np.abs(av.astype(np.float64) - ref_av) / np.abs(ref_av)) < AV_RTOL_REF
 
 
 def assert_parity(sim, oracle, pkg, cells0, obstacles, iters, **kw):
-    ref_cells, ref_av = oracle_run(oracle, pkg, cells0, obstacles, iters, **kw)
+    ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, iters, **kw)
     av = sim.run(iters)
     got = sim.get_cells()
     mism = np.argwhere(bits(got) != bits(ref_cells))
     assert mism.size == 0, f"{len(mism)} populations differ, first at (y,x,k)={mism[0].tolist()}"
-    if iters:
-        assert np.max(np.abs(av.astype(np.float64) - ref_av) / np.abs(ref_av)) < AV_RTOL
+    assert_av(av, ref_av, ref_exact)
     return ref_cells
 
 
@@ -84,12 +92,12 @@ def test_runs_compose(pkg, oracle):
     nx, ny = 256, 20
     obstacles = random_obstacles(rng, ny, nx, 0.05)
     cells0 = random_cells(rng, ny, nx)
-    ref_cells, ref_av = oracle_run(oracle, pkg, cells0, obstacles, 14)
+    ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, 14)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         sim.set_cells(cells0)
         av = np.concatenate([sim.run(7), sim.run(6), sim.run(0), sim.run(1)])
         assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
-        assert np.max(np.abs(av - ref_av) / ref_av) < AV_RTOL
+        assert_av(av, ref_av, ref_exact)
 
 
 @pytest.mark.parametrize("min_ctas,ctas_per_sm", [(2, 0), (3, 0), (2, 1)])
