@@ -101,7 +101,7 @@ struct lbm_b200 {
   int cur = 0;                          // index of the buffer holding the current state
   std::vector<Slab> slabs;
   // options
-  long opt_kernel = 0, opt_graph_steps = 0, opt_ctas_per_sm = 0, opt_min_ctas = 2;
+  long opt_kernel = 0, opt_graph_steps = 0, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0;
   int last_iters = 0;
   int graph_len = 0;
   long launches = 0;                    // kernels launched by the last enqueue (all slabs)
@@ -139,8 +139,9 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
     *threads = (int)warps * 32;
     int per_sm = (int)h->opt_ctas_per_sm;
     if (per_sm <= 0) {
-      per_sm = (h->opt_min_ctas >= 3) ? occupancy(lbm::step_vec4<false, 3>, *threads)
-                                      : occupancy(lbm::step_vec4<false, 2>, *threads);
+      per_sm = (h->opt_min_ctas >= 4)   ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
+               : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
+                                        : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
     }
     const long want = (nseg + warps - 1) / warps;
     *grid = (int)std::max(1L, std::min(want, (long)sms * per_sm));
@@ -268,8 +269,18 @@ int launch_step(lbm_b200* h, const Slab& s, const StepArgs& a, int grid, int thr
   if (grid <= 0) return LBM_B200_OK;
   h->launches++;
   if (use_vec4(h)) {
-    if (h->opt_min_ctas >= 3) lbm::step_vec4<PEER, 3><<<grid, threads, 0, s.stream>>>(a);
-    else lbm::step_vec4<PEER, 2><<<grid, threads, 0, s.stream>>>(a);
+#define LBM_LAUNCH_VEC4(M, H) lbm::step_vec4<PEER, M, H><<<grid, threads, 0, s.stream>>>(a)
+#define LBM_LAUNCH_HINT(M)                                                                     \
+  do {                                                                                         \
+    if (h->opt_cache_hint == 1) LBM_LAUNCH_VEC4(M, 1);                                         \
+    else if (h->opt_cache_hint == 2) LBM_LAUNCH_VEC4(M, 2);                                    \
+    else LBM_LAUNCH_VEC4(M, 0);                                                                \
+  } while (0)
+    if (h->opt_min_ctas >= 4) LBM_LAUNCH_HINT(4);
+    else if (h->opt_min_ctas == 3) LBM_LAUNCH_HINT(3);
+    else LBM_LAUNCH_HINT(2);
+#undef LBM_LAUNCH_HINT
+#undef LBM_LAUNCH_VEC4
   } else {
     lbm::step_scalar<PEER><<<grid, threads, 0, s.stream>>>(a);
   }
@@ -397,6 +408,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_GRAPH_STEPS")) h->opt_graph_steps = atol(e);
   if (const char* e = getenv("LBM_B200_CTAS_PER_SM")) h->opt_ctas_per_sm = atol(e);
   if (const char* e = getenv("LBM_B200_MIN_CTAS")) h->opt_min_ctas = atol(e);
+  if (const char* e = getenv("LBM_B200_CACHE_HINT")) h->opt_cache_hint = atol(e);
 }
 
 }  // namespace
@@ -811,8 +823,11 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < 0 || value > 32) return fail(LBM_B200_ERR_ARG, "ctas_per_sm must be 0..32");
     h->opt_ctas_per_sm = value;
   } else if (!strcmp(key, "min_ctas")) {
-    if (value != 2 && value != 3) return fail(LBM_B200_ERR_ARG, "min_ctas must be 2 or 3");
+    if (value < 2 || value > 4) return fail(LBM_B200_ERR_ARG, "min_ctas must be 2, 3 or 4");
     h->opt_min_ctas = value;
+  } else if (!strcmp(key, "cache_hint")) {
+    if (value < 0 || value > 2) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1 or 2");
+    h->opt_cache_hint = value;
   } else {
     return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);
   }
@@ -829,6 +844,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;
   else if (!strcmp(key, "ctas_per_sm")) *value = h->opt_ctas_per_sm;
   else if (!strcmp(key, "min_ctas")) *value = h->opt_min_ctas;
+  else if (!strcmp(key, "cache_hint")) *value = h->opt_cache_hint;
   else if (!strcmp(key, "grid")) *value = h->slabs[0].per_step;
   else if (!strcmp(key, "threads")) *value = h->n_ranks == 1 ? h->slabs[0].threads_full : h->slabs[0].threads_int;
   else if (!strcmp(key, "launches_per_step")) *value = h->n_ranks == 1 ? 1 : 2;

@@ -83,6 +83,29 @@ __device__ __forceinline__ void peer_signal(const StepArgs& a)
   }
 }
 
+// Global access flavours of the vec4 kernel (template parameter HINT):
+//   0  ld.global.nc (read-only path) + plain st.global
+//   1  ld.global.cs + st.global.cs   (streaming: evict-first in L1 and L2)
+//   2  ld.global.nc + st.global.cs
+template <int HINT>
+__device__ __forceinline__ float4 load4(const float* p)
+{
+  if (HINT == 1) return __ldcs(reinterpret_cast<const float4*>(p));
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <int HINT>
+__device__ __forceinline__ float load1(const float* p)
+{
+  if (HINT == 1) return __ldcs(p);
+  return __ldg(p);
+}
+template <int HINT>
+__device__ __forceinline__ void store4(float* p, float4 v)
+{
+  if (HINT == 0) *reinterpret_cast<float4*>(p) = v;
+  else __stcs(reinterpret_cast<float4*>(p), v);
+}
+
 // Sum of `v` over the CTA, written by thread 0 to *out.  Deterministic (fixed tree).
 __device__ __forceinline__ void block_sum_to(double v, double* out)
 {
@@ -108,7 +131,7 @@ __device__ __forceinline__ void block_sum_to(double v, double* out)
 // lanes of a segment fetch one extra scalar across the segment (or the periodic) boundary.
 // Persistent grid: CTAs stride over the segments.  Requires nx % 4 == 0, nx >= 8.
 // ---------------------------------------------------------------------------------------
-template <bool PEER, int MIN_CTAS>
+template <bool PEER, int MIN_CTAS, int HINT>
 __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 {
   if (PEER) peer_wait(a);
@@ -140,21 +163,21 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
     float e_c = 0.f, e_s = 0.f, e_n = 0.f;
     uint32_t mw = 0;
     if (active) {
-      c[0] = __ldg(reinterpret_cast<const float4*>(src + 0 * P + o_c + x0));
-      c[1] = __ldg(reinterpret_cast<const float4*>(src + 1 * P + o_c + x0));
-      c[2] = __ldg(reinterpret_cast<const float4*>(src + 2 * P + o_s + x0));
-      c[3] = __ldg(reinterpret_cast<const float4*>(src + 3 * P + o_c + x0));
-      c[4] = __ldg(reinterpret_cast<const float4*>(src + 4 * P + o_n + x0));
-      c[5] = __ldg(reinterpret_cast<const float4*>(src + 5 * P + o_s + x0));
-      c[6] = __ldg(reinterpret_cast<const float4*>(src + 6 * P + o_s + x0));
-      c[7] = __ldg(reinterpret_cast<const float4*>(src + 7 * P + o_n + x0));
-      c[8] = __ldg(reinterpret_cast<const float4*>(src + 8 * P + o_n + x0));
+      c[0] = load4<HINT>(src + 0 * P + o_c + x0);
+      c[1] = load4<HINT>(src + 1 * P + o_c + x0);
+      c[2] = load4<HINT>(src + 2 * P + o_s + x0);
+      c[3] = load4<HINT>(src + 3 * P + o_c + x0);
+      c[4] = load4<HINT>(src + 4 * P + o_n + x0);
+      c[5] = load4<HINT>(src + 5 * P + o_s + x0);
+      c[6] = load4<HINT>(src + 6 * P + o_s + x0);
+      c[7] = load4<HINT>(src + 7 * P + o_n + x0);
+      c[8] = load4<HINT>(src + 8 * P + o_n + x0);
       mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5));
       if (west_edge || east_edge) {
         // west end: populations 1, 5, 8 arrive from x-1; east end: 3, 6, 7 arrive from x+1
-        e_c = __ldg(west_edge ? src + 1 * P + o_c + xw : src + 3 * P + o_c + xe);
-        e_s = __ldg(west_edge ? src + 5 * P + o_s + xw : src + 6 * P + o_s + xe);
-        e_n = __ldg(west_edge ? src + 8 * P + o_n + xw : src + 7 * P + o_n + xe);
+        e_c = load1<HINT>(west_edge ? src + 1 * P + o_c + xw : src + 3 * P + o_c + xe);
+        e_s = load1<HINT>(west_edge ? src + 5 * P + o_s + xw : src + 6 * P + o_s + xe);
+        e_n = load1<HINT>(west_edge ? src + 8 * P + o_n + xw : src + 7 * P + o_n + xe);
       }
     } else {
 #pragma unroll
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 
 #pragma unroll
       for (int k = 0; k < 9; k++)
-        *reinterpret_cast<float4*>(dst + k * P + o_c + x0) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+        store4<HINT>(dst + k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
 
       if (PEER) {
         // one-row halo exchange: NVLink stores straight into the neighbour's halo row

@@ -100,8 +100,8 @@ def test_runs_compose(pkg, oracle):
         assert_av(av, ref_av, ref_exact)
 
 
-@pytest.mark.parametrize("min_ctas,ctas_per_sm", [(2, 0), (3, 0), (2, 1)])
-def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per_sm):
+@pytest.mark.parametrize("min_ctas,ctas_per_sm,hint", [(2, 0, 0), (3, 0, 1), (2, 1, 2), (4, 7, 0)])
+def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per_sm, hint):
     rng = np.random.default_rng(11)
     nx, ny = 1024, 40
     obstacles = random_obstacles(rng, ny, nx, 0.03)
@@ -109,6 +109,7 @@ def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         sim.set_option("min_ctas", min_ctas)
         sim.set_option("ctas_per_sm", ctas_per_sm)
+        sim.set_option("cache_hint", hint)
         sim.set_cells(cells0)
         assert_parity(sim, oracle, pkg, cells0, obstacles, 9)
 
