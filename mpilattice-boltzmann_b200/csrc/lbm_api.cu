@@ -820,7 +820,7 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < 0) return fail(LBM_B200_ERR_ARG, "graph_steps must be >= 0");
     h->opt_graph_steps = value;
   } else if (!strcmp(key, "ctas_per_sm")) {
-    if (value < 0 || value > 32) return fail(LBM_B200_ERR_ARG, "ctas_per_sm must be 0..32");
+    if (value < 0 || value > 65536) return fail(LBM_B200_ERR_ARG, "ctas_per_sm must be 0..65536");
     h->opt_ctas_per_sm = value;
   } else if (!strcmp(key, "min_ctas")) {
     if (value < 2 || value > 4) return fail(LBM_B200_ERR_ARG, "min_ctas must be 2, 3 or 4");
@@ -857,9 +857,13 @@ void lbm_b200_destroy(lbm_b200* h)
 {
   if (!h) return;
   destroy_graphs(h);
+  // slabs may share a stream: drain everything first, free memory, destroy streams last
   for (Slab& s : h->slabs) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+  }
+  for (Slab& s : h->slabs) {
+    cudaSetDevice(s.device);
     for (Neighbour* n : {&s.south, &s.north}) {
       if (!n->ipc) continue;
       for (int i = 0; i < 2; i++)
@@ -875,7 +879,11 @@ void lbm_b200_destroy(lbm_b200* h)
     if (s.cursor) cudaFree(s.cursor);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
-    if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+  }
+  for (Slab& s : h->slabs) {
+    if (!s.own_stream || !s.stream) continue;
+    cudaSetDevice(s.device);
+    cudaStreamDestroy(s.stream);
   }
   cudaGetLastError();
   delete h;
