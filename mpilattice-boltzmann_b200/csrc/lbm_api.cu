@@ -85,6 +85,7 @@ struct IpcBlob {
   int pid;
 };
 
+constexpr int kOversubscribe = 64;      // queued CTAs per resident CTA slot of the persistent grid
 constexpr int kChunkSteps = 256;        // steps whose CTA partials are kept before one reduce launch
 
 }  // namespace
@@ -142,6 +143,10 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
       per_sm = (h->opt_min_ctas >= 4)   ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
                : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
                                         : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
+      // Oversubscribe: ~64 CTAs queued per resident slot lets the hardware scheduler balance
+      // the two dies (measured on 16384^2: 84.3 GLUPS at 1x, 88.9 at 64x, 81.3 at 512x;
+      // profiles/r01_sweep.md), while each warp still strides over >= ~14 segments.
+      per_sm *= kOversubscribe;
     }
     const long want = (nseg + warps - 1) / warps;
     *grid = (int)std::max(1L, std::min(want, (long)sms * per_sm));
