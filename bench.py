@@ -182,14 +182,17 @@ def bench_reference(args, pkg):
 # our arm
 # ----------------------------------------------------------------------------------------
 def workload_config(args, n):
+    strong = getattr(args, "scaling", "weak") == "strong"
+    ny_global = args.ny if strong else args.ny * n
+    per_gpu = f"{args.nx}x{ny_global // n}" if strong else f"{args.nx}x{args.ny}"
     return {
-        "workload": f"synthetic channel {args.nx}x{args.ny} cells per GPU (global {args.nx}x{args.ny * n}, "
+        "workload": f"synthetic channel {per_gpu} cells per GPU (global {args.nx}x{ny_global}, "
                     f"{n} row slab(s)), walls on rows 0 and ny-1, x periodic, accel on row ny-2",
-        "nx": args.nx, "ny_per_gpu": args.ny, "ny_global": args.ny * n,
+        "nx": args.nx, "ny_per_gpu": ny_global // n, "ny_global": ny_global,
         "timesteps_per_step": args.timesteps,
         "density": DENSITY, "accel": ACCEL, "omega": OMEGA,
         "layout": "fp32 SoA, 9 planes, ping-pong; 1-bit obstacle mask",
-        "l2": f"no L2 flush needed: {2 * 9 * 4 * args.nx * args.ny / 1e9:.1f} GB of state per GPU streams through the 126 MB L2 every timestep",
+        "l2": f"no L2 flush needed: {2 * 9 * 4 * args.nx * (ny_global // n) / 1e9:.1f} GB of state per GPU streams through the 126 MB L2 every timestep",
         "parallelism": f"row-slab x{n}" + (", halo rows as NVLink stores from the edge-row kernel" if n > 1 else ""),
     }
 
@@ -243,9 +246,12 @@ def bench_ours(args, pkg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    nx, rows, n = args.nx, args.ny, world
-    ny_global = rows * n
-    first = rank * rows
+    nx, n = args.nx, world
+    if args.scaling == "strong":
+        split_rows, split_first = pkg.decompose(args.ny, n)
+        rows, first, ny_global = int(split_rows[rank]), int(split_first[rank]), args.ny
+    else:
+        rows, ny_global, first = args.ny, args.ny * n, rank * args.ny
     ips, K, W = args.timesteps, args.steps, args.warmup
     free = nx * (ny_global - 2)
     inv = float(np.float32(1.0) / np.float32(free))
@@ -335,7 +341,7 @@ def bench_ours(args, pkg):
     if rank == 0:
         line = {
             "metric": "MLUPS", "value": round(value, 1), "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W,
-            "ms_per_step": round(device_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(device_ms / K, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "kernel": {1: "step_scalar", 2: "step_vec4"}.get(kernel, str(kernel)),
             "wall_ms_per_step": round(wall_s * 1e3 / K, 4),
@@ -375,6 +381,8 @@ def main():
     ap.add_argument("--ctas-per-sm", dest="ctas_per_sm", type=int, default=None)
     ap.add_argument("--min-ctas", dest="min_ctas", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --ny rows per GPU (default); strong: --ny rows in total, split over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                               # timing rule: at least 3 warm-up steps
