@@ -135,7 +135,8 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
 
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
  *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit)
- *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches)
+ *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches, -1 = automatic:
+ *                   graphs of 256 steps for single-GPU grids of up to 2^22 cells)
  *   "ctas_per_sm"   persistent-grid size in CTAs per SM (0 = occupancy query)
  *   "min_ctas"      register budget of the 128-bit kernel: 2, 3 or 4 resident CTAs per SM
  *   "cache_hint"    0 = read-only loads + plain stores, 1 = streaming loads and stores,
