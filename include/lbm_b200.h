@@ -134,7 +134,11 @@ int lbm_b200_set_cells(lbm_b200* handle, const float* cells);
 int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u, float* pressure);
 
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
- *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit)
+ *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit); reads back 3
+ *                   when the resident variant of kernel 2 is in use
+ *   "resident"      1 = run up to 256 timesteps per cooperative launch with a grid-wide barrier between
+ *                   steps (for launch-latency-bound grids), 0 = never, -1 = automatic (single-GPU grids of
+ *                   up to 2^22 cells)
  *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches, -1 = automatic:
  *                   graphs of 256 steps for single-GPU grids of up to 2^22 cells)
  *   "ctas_per_sm"   persistent-grid size in CTAs per SM (0 = occupancy query)

@@ -103,7 +103,8 @@ struct lbm_b200 {
   int cur = 0;                          // index of the buffer holding the current state
   std::vector<Slab> slabs;
   // options
-  long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0;
+  long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
+  bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   int last_iters = 0;
   int graph_len = 0;
   long launches = 0;                    // kernels launched by the last enqueue (all slabs)
@@ -129,7 +130,7 @@ int occupancy(K kernel, int threads)
 }
 
 // persistent-grid geometry for `rows` rows of the slab
-void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* grid)
+void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* grid, bool resident = false)
 {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -140,7 +141,11 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
     warps = std::max(1L, std::min(8L, warps));
     *threads = (int)warps * 32;
     int per_sm = (int)h->opt_ctas_per_sm;
-    if (per_sm <= 0) {
+    if (resident) {
+      // every CTA must be co-resident for the grid-wide barrier
+      const int fit = occupancy(lbm::steps_resident<2>, *threads);
+      per_sm = per_sm > 0 ? std::min(per_sm, fit) : fit;
+    } else if (per_sm <= 0) {
       per_sm = (h->opt_min_ctas >= 4)   ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
                : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
                                         : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
@@ -161,11 +166,22 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
   }
 }
 
+// The resident kernel pays off where a step is only a few microseconds of work (launch latency bound).
+bool want_resident(const lbm_b200* h)
+{
+  if (h->opt_resident == 0 || h->n_ranks != 1 || h->slabs.size() != 1 || !use_vec4(h)) return false;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->slabs[0].device);
+  if (!coop) return false;
+  return h->opt_resident == 1 || (long)h->nx * h->ny <= kGraphAutoCells;
+}
+
 void plan(lbm_b200* h)
 {
+  h->resident = want_resident(h);
   for (Slab& s : h->slabs) {
     if (h->n_ranks == 1) {
-      plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
+      plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
       s.per_step = s.grid_full;
     } else {
@@ -204,17 +220,19 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   CUDA_TRY(cudaEventCreate(&s.ev_start));
   CUDA_TRY(cudaEventCreate(&s.ev_stop));
 
-  // bit-pack the obstacle rows: 32 cells per word, rows padded to whole words
+  // obstacle rows: upload the reference's int-per-cell array into the (still unused) second population
+  // buffer and bit-pack it on the device: 32 cells per word, rows padded to whole words
   const size_t words = (size_t)s.rows * h->mask_row_words;
-  std::vector<uint32_t> packed(words, 0u);
-  for (int r = 0; r < s.rows; r++) {
-    const int* row = obstacles_rows + (size_t)r * h->nx;
-    uint32_t* out = packed.data() + (size_t)r * h->mask_row_words;
-    for (int x = 0; x < h->nx; x++)
-      if (row[x]) out[x >> 5] |= 1u << (x & 31);
-  }
+  const size_t cells = (size_t)s.rows * h->nx;
   CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
-  CUDA_TRY(cudaMemcpy(s.mask, packed.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  int* staged = reinterpret_cast<int*>(s.buf[1]);
+  CUDA_TRY(cudaMemcpyAsync(staged, obstacles_rows, cells * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  {
+    const long warps = (long)s.rows * ((h->mask_row_words + 31) / 32);
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    lbm::pack_mask<<<blocks, 256, 0, s.stream>>>(staged, h->nx, s.rows, h->mask_row_words, s.mask);
+    CUDA_TRY(cudaGetLastError());
+  }
 
   // uniform initial state in both buffers, halo rows included (d2q9-bgk.c:880-902)
   const float w0 = h->density * 4.0f / 9.0f, w1 = h->density / 9.0f, w2 = h->density / 36.0f;
@@ -415,6 +433,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_CTAS_PER_SM")) h->opt_ctas_per_sm = atol(e);
   if (const char* e = getenv("LBM_B200_MIN_CTAS")) h->opt_min_ctas = atol(e);
   if (const char* e = getenv("LBM_B200_CACHE_HINT")) h->opt_cache_hint = atol(e);
+  if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
 }
 
 }  // namespace
@@ -635,6 +654,7 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
     CUDA_TRY(cudaMemsetAsync(s.cursor, 0, sizeof(unsigned), s.stream));
   }
   int glen = (int)h->opt_graph_steps;
+  if (h->resident) glen = 0;
   if (glen < 0) {
     // auto: grids whose step kernel is launch-latency bound (a few microseconds) are replayed
     // from CUDA graphs -- measured 4.1 -> 2.7 us per step on the 128..256-wide decks
@@ -667,6 +687,27 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       h->launches++;
     }
     int t = 0;
+    if (h->resident) {
+      // many steps per cooperative launch; the buffers swap roles inside the kernel
+      Slab& s = h->slabs[0];
+      CUDA_TRY(cudaSetDevice(s.device));
+      while (t < iters) {
+        const int n = std::min(kChunkSteps, iters - t);
+        StepArgs a = base_args(h, s, 0, true);
+        a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+        a.south_of_first = s.rows;
+        a.north_of_last = 1;
+        lbm::ResidentArgs r{s.buf[h->cur], s.buf[h->cur ^ 1], n, t + n != iters, s.per_step};
+        void* params[] = {&a, &r};
+        CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::steps_resident<2>), dim3(s.grid_full),
+                                             dim3(s.threads_full), params, 0, s.stream));
+        h->launches++;
+        h->cur ^= (n & 1);
+        int rc = enqueue_reduce(h, n);
+        if (rc) return rc;
+        t += n;
+      }
+    }
     if (glen >= 2 && h->graph_len == glen) {
       Slab& s = h->slabs[0];
       while (iters - 1 - t >= glen) {                // the very last step never folds a force in
@@ -838,6 +879,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "min_ctas")) {
     if (value < 2 || value > 4) return fail(LBM_B200_ERR_ARG, "min_ctas must be 2, 3 or 4");
     h->opt_min_ctas = value;
+  } else if (!strcmp(key, "resident")) {
+    if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "resident must be -1, 0 or 1");
+    h->opt_resident = value;
   } else if (!strcmp(key, "cache_hint")) {
     if (value < 0 || value > 2) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1 or 2");
     h->opt_cache_hint = value;
@@ -853,11 +897,12 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
 {
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
-  if (!strcmp(key, "kernel")) *value = use_vec4(h) ? 2 : 1;
+  if (!strcmp(key, "kernel")) *value = h->resident ? 3 : (use_vec4(h) ? 2 : 1);
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;
   else if (!strcmp(key, "ctas_per_sm")) *value = h->opt_ctas_per_sm;
   else if (!strcmp(key, "min_ctas")) *value = h->opt_min_ctas;
   else if (!strcmp(key, "cache_hint")) *value = h->opt_cache_hint;
+  else if (!strcmp(key, "resident")) *value = h->resident ? 1 : 0;
   else if (!strcmp(key, "grid")) *value = h->slabs[0].per_step;
   else if (!strcmp(key, "threads")) *value = h->n_ranks == 1 ? h->slabs[0].threads_full : h->slabs[0].threads_int;
   else if (!strcmp(key, "launches_per_step")) *value = h->n_ranks == 1 ? 1 : 2;

@@ -8,6 +8,7 @@
 // whole words.  Algorithmic traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include "lbm_cell.cuh"
 
@@ -87,22 +88,25 @@ __device__ __forceinline__ void peer_signal(const StepArgs& a)
 //   0  ld.global.nc (read-only path) + plain st.global
 //   1  ld.global.cs + st.global.cs   (streaming: evict-first in L1 and L2)
 //   2  ld.global.nc + st.global.cs
+//   3  ld.global.cg (L2 only, coherent within a launch) + plain st.global   [resident kernel]
 template <int HINT>
 __device__ __forceinline__ float4 load4(const float* p)
 {
   if (HINT == 1) return __ldcs(reinterpret_cast<const float4*>(p));
+  if (HINT == 3) return __ldcg(reinterpret_cast<const float4*>(p));
   return __ldg(reinterpret_cast<const float4*>(p));
 }
 template <int HINT>
 __device__ __forceinline__ float load1(const float* p)
 {
   if (HINT == 1) return __ldcs(p);
+  if (HINT == 3) return __ldcg(p);
   return __ldg(p);
 }
 template <int HINT>
 __device__ __forceinline__ void store4(float* p, float4 v)
 {
-  if (HINT == 0) *reinterpret_cast<float4*>(p) = v;
+  if (HINT == 0 || HINT == 3) *reinterpret_cast<float4*>(p) = v;
   else __stcs(reinterpret_cast<float4*>(p), v);
 }
 
@@ -131,16 +135,15 @@ __device__ __forceinline__ void block_sum_to(double v, double* out)
 // lanes of a segment fetch one extra scalar across the segment (or the periodic) boundary.
 // Persistent grid: CTAs stride over the segments.  Requires nx % 4 == 0, nx >= 8.
 // ---------------------------------------------------------------------------------------
-template <bool PEER, int MIN_CTAS, int HINT>
-__global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
+// One pass of this CTA over its share of the row segments: src -> dst.  Returns the thread's share of
+// Sigma |m|/rho.  `accel_row` = padded row that gets the next step's body force folded in (or -1).
+template <bool PEER, int HINT>
+__device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __restrict__ src, float* __restrict__ dst,
+                                            const int accel_row)
 {
-  if (PEER) peer_wait(a);
-
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const long nseg = (long)a.row_count * a.chunks;
-  const float* __restrict__ src = a.src;
-  float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
   double acc = 0.0;
 
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 
     if (active) {
       const unsigned bits = (mw >> (x0 & 31)) & 0xFu;
-      const bool fold_accel = (row == a.accel_row);
+      const bool fold_accel = (row == accel_row);
       float f[4][9];
       f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
       f[0][1] = w1v;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
@@ -242,8 +245,44 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
     }
   }
 
+  return acc;
+}
+
+template <bool PEER, int MIN_CTAS, int HINT>
+__global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
+{
+  if (PEER) peer_wait(a);
+  const double acc = vec4_pass<PEER, HINT>(a, a.src, a.dst, a.accel_row);
   block_sum_to(acc, a.partials + blockIdx.x);
   if (PEER) peer_signal(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 3 ("resident"): many timesteps in ONE cooperative launch for grids that are launch-latency
+// bound (the shipped 128..1024-wide decks: a step is a few microseconds of work).  The same pass as
+// step_vec4 runs `steps` times with a grid-wide barrier in between and the two buffers swapping roles;
+// loads bypass L1 (ld.global.cg) so every step sees what other SMs stored in the previous one.
+// ---------------------------------------------------------------------------------------
+struct ResidentArgs {
+  float* buf0;       // holds the current state at launch
+  float* buf1;
+  int steps;         // timesteps in this launch (<= the partials capacity)
+  int fold_last;     // whether the last of them folds the next step's body force in
+  int partial_stride;  // doubles between consecutive steps' partials (= grid size)
+};
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) steps_resident(const StepArgs a, const ResidentArgs r)
+{
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  for (int t = 0; t < r.steps; t++) {
+    const float* src = (t & 1) ? r.buf1 : r.buf0;
+    float* dst = (t & 1) ? r.buf0 : r.buf1;
+    const int accel_row = (t + 1 < r.steps || r.fold_last) ? a.accel_row : -1;
+    const double acc = vec4_pass<false, 3>(a, src, dst, accel_row);
+    block_sum_to(acc, a.partials + (size_t)t * r.partial_stride + blockIdx.x);
+    grid.sync();
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -353,6 +392,26 @@ __global__ void reduce_partials(const double* partials, int per_step, int steps,
   }
 }
 __global__ void advance_cursor(unsigned* cursor, unsigned by) { *cursor += by; }
+
+// int-per-cell obstacle rows (the reference's layout, d2q9-bgk.c:875) -> 1 bit per cell.  One warp packs
+// 32 words of one row at a time: coalesced 128 B reads, one ballot per word.
+__global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words, uint32_t* mask)
+{
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int groups = (row_words + 31) / 32;                 // 32-word groups per row
+  if (warp >= (long)rows * groups) return;
+  const int r = (int)(warp / groups);
+  const int w0 = (int)(warp - (long)r * groups) * 32;
+  const int* row = obstacles + (size_t)r * nx;
+  uint32_t mine = 0;
+  for (int i = 0; i < 32; i++) {
+    const int x = (w0 + i) * 32 + lane;
+    const unsigned word = __ballot_sync(0xffffffffu, x < nx && row[x] != 0);
+    if (i == lane) mine = word;
+  }
+  if (w0 + lane < row_words) mask[(size_t)r * row_words + w0 + lane] = mine;
+}
 
 // uniform initial state, every padded row (d2q9-bgk.c:880-902)
 __global__ void fill_planes(float* buf, size_t plane, float w0, float w1, float w2)

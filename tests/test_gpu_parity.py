@@ -49,13 +49,14 @@ def test_uniform_start_bit_exact(pkg, oracle, nx, ny):
     rng = np.random.default_rng(nx * 131 + ny)
     obstacles = random_obstacles(rng, ny, nx, 0.06)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
-        assert sim.get_option("kernel") == (2 if nx % 4 == 0 and nx >= 8 else 1)
+        # small single-GPU grids run the resident (cooperative, many steps per launch) variant of the 128-bit kernel
+        assert sim.get_option("kernel") == (3 if nx % 4 == 0 and nx >= 8 else 1)
         cells0 = oracle.init_cells(nx, ny, DENSITY)
         assert np.array_equal(bits(sim.get_cells()), bits(cells0))     # initialise(): d2q9-bgk.c:880-902
         assert_parity(sim, oracle, pkg, cells0, obstacles, 30)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("nx,ny,walls", [(128, 24, True), (136, 19, False), (256, 7, False)])
 def test_random_state_bit_exact(pkg, oracle, kernel, nx, ny, walls):
     """Arbitrary positive states, obstacles on every edge, open top/bottom rows (y-wrap), x-wrap."""
@@ -65,7 +66,9 @@ def test_random_state_bit_exact(pkg, oracle, kernel, nx, ny, walls):
     obstacles[:, -1] = rng.random(ny) < 0.5
     cells0 = random_cells(rng, ny, nx)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
-        sim.set_option("kernel", kernel)
+        sim.set_option("resident", 1 if kernel == 3 else 0)
+        sim.set_option("kernel", min(kernel, 2))
+        assert sim.get_option("kernel") == kernel
         sim.set_cells(cells0)
         assert np.array_equal(bits(sim.get_cells()), bits(cells0))
         assert_parity(sim, oracle, pkg, cells0, obstacles, 17)
@@ -107,6 +110,7 @@ def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per
     obstacles = random_obstacles(rng, ny, nx, 0.03)
     cells0 = random_cells(rng, ny, nx)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("resident", 0)
         sim.set_option("min_ctas", min_ctas)
         sim.set_option("ctas_per_sm", ctas_per_sm)
         sim.set_option("cache_hint", hint)
@@ -121,9 +125,25 @@ def test_cuda_graph_replay_is_identical(pkg, oracle, graph_steps, iters):
     obstacles = random_obstacles(rng, ny, nx, 0.05)
     cells0 = random_cells(rng, ny, nx)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("resident", 0)
         sim.set_option("graph_steps", graph_steps)
         sim.set_cells(cells0)
         assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+
+
+@pytest.mark.parametrize("nx,ny,iters", [(128, 16, 300), (1024, 40, 513), (256, 256, 257), (8, 8, 31)])
+def test_resident_kernel_many_steps_per_launch(pkg, oracle, nx, ny, iters):
+    """The cooperative kernel: up to 256 steps per launch with a grid barrier in between; odd step counts
+    (buffer parity), chunk boundaries (256/257/513) and a grid larger than the co-resident CTA count."""
+    rng = np.random.default_rng(nx + iters)
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("resident", 1)
+        assert sim.get_option("kernel") == 3
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+        assert sim.get_option("launches") <= 3 * ((iters + 255) // 256) + 1
 
 
 def test_av_vels_is_deterministic(pkg):

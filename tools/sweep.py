@@ -29,15 +29,17 @@ def main():
     ap.add_argument("--ctas-per-sm", default="0")
     ap.add_argument("--hints", default="0,1,2")
     ap.add_argument("--graph-steps", default="0")
+    ap.add_argument("--resident", default="0")
     args = ap.parse_args()
     pkg = entry.load_package()
     obstacles = pkg.decks.channel_obstacles(args.nx, args.ny)
     results = []
     with pkg.Simulation(args.nx, args.ny, 0.1, 0.005, 1.85, obstacles) as sim:
-        lists = [[int(v) for v in s.split(",")] for s in (args.kernels, args.min_ctas, args.ctas_per_sm, args.hints, args.graph_steps)]
-        for kernel, min_ctas, per_sm, hint, graph in itertools.product(*lists):
+        lists = [[int(v) for v in s.split(",")] for s in (args.kernels, args.min_ctas, args.ctas_per_sm, args.hints, args.graph_steps, args.resident)]
+        for kernel, min_ctas, per_sm, hint, graph, resident in itertools.product(*lists):
             if kernel == 1 and (min_ctas != lists[1][0] or hint != lists[3][0]):
                 continue
+            sim.set_option("resident", resident)
             sim.set_option("kernel", kernel)
             sim.set_option("min_ctas", min_ctas)
             sim.set_option("ctas_per_sm", per_sm)
@@ -50,7 +52,7 @@ def main():
                 ms = sim.elapsed_ms()
                 best = ms if best is None else min(best, ms)
             mlups = args.nx * args.ny * args.timesteps / (best * 1e-3) / 1e6
-            rec = {"kernel": kernel, "min_ctas": min_ctas, "ctas_per_sm": per_sm, "cache_hint": hint, "graph_steps": graph,
+            rec = {"kernel": kernel, "min_ctas": min_ctas, "ctas_per_sm": per_sm, "cache_hint": hint, "graph_steps": graph, "resident": resident,
                    "grid": sim.get_option("grid"), "threads": sim.get_option("threads"),
                    "us_per_step": round(best * 1e3 / args.timesteps, 2), "mlups": round(mlups, 1),
                    "gbs": round(mlups * 72e-3, 1)}
