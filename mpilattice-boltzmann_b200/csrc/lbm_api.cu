@@ -85,7 +85,8 @@ struct IpcBlob {
   int pid;
 };
 
-constexpr int kOversubscribe = 64;      // queued CTAs per resident CTA slot of the persistent grid
+constexpr int kMaxCtasPerSm = 128;      // upper bound of the oversubscribed grid, in CTAs per SM
+constexpr long kResidentAutoMinCells = 1L << 18;
 constexpr long kGraphAutoCells = 1L << 22;  // up to 2048^2: step kernel <= ~60 us, launch gaps matter
 constexpr int kChunkSteps = 256;        // steps whose CTA partials are kept before one reduce launch
 
@@ -149,10 +150,11 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
       per_sm = (h->opt_min_ctas >= 4)   ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
                : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
                                         : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
-      // Oversubscribe: ~64 CTAs queued per resident slot lets the hardware scheduler balance
-      // the two dies (measured on 16384^2: 84.3 GLUPS at 1x, 88.9 at 64x, 81.3 at 512x;
-      // profiles/r01_sweep.md), while each warp still strides over >= ~14 segments.
-      per_sm *= kOversubscribe;
+      // Oversubscribe the resident slots so the hardware CTA scheduler balances the two dies, but keep
+      // enough segments per warp to amortise the CTA prologue and block reduction.  Measured optimum
+      // (profiles/r01_sweep.md): 128 CTAs/SM at 16384 rows x 16384, 16-32 at 4096 rows, 2-16 at 2048 rows
+      // -> CTAs per SM = segments / 16384, clamped to [resident slots, 128].
+      per_sm = (int)std::max<long>(per_sm, std::min<long>(kMaxCtasPerSm, nseg >> 14));
     }
     const long want = (nseg + warps - 1) / warps;
     *grid = (int)std::max(1L, std::min(want, (long)sms * per_sm));
@@ -173,7 +175,10 @@ bool want_resident(const lbm_b200* h)
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->slabs[0].device);
   if (!coop) return false;
-  return h->opt_resident == 1 || (long)h->nx * h->ny <= kGraphAutoCells;
+  // measured (profiles/r01_summary.md): below ~512^2 a CUDA graph of plain launches is as fast or faster
+  // (2.7 vs 2.9 us per step); from 1024^2 to 2048^2 the resident kernel wins by 16-25 %
+  const long cells = (long)h->nx * h->ny;
+  return h->opt_resident == 1 || (cells >= kResidentAutoMinCells && cells <= kGraphAutoCells);
 }
 
 void plan(lbm_b200* h)

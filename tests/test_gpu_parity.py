@@ -49,8 +49,9 @@ def test_uniform_start_bit_exact(pkg, oracle, nx, ny):
     rng = np.random.default_rng(nx * 131 + ny)
     obstacles = random_obstacles(rng, ny, nx, 0.06)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
-        # small single-GPU grids run the resident (cooperative, many steps per launch) variant of the 128-bit kernel
-        assert sim.get_option("kernel") == (3 if nx % 4 == 0 and nx >= 8 else 1)
+        # 128-bit kernel whenever nx allows it; its resident (cooperative, many steps per launch) variant
+        # is the automatic choice only from 2^18 cells
+        assert sim.get_option("kernel") == (2 if nx % 4 == 0 and nx >= 8 else 1)
         cells0 = oracle.init_cells(nx, ny, DENSITY)
         assert np.array_equal(bits(sim.get_cells()), bits(cells0))     # initialise(): d2q9-bgk.c:880-902
         assert_parity(sim, oracle, pkg, cells0, obstacles, 30)
