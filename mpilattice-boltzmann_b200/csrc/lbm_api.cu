@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include <time.h>
 #include <unistd.h>
 
 #include <cuda_runtime.h>
@@ -208,8 +209,17 @@ void destroy_graphs(lbm_b200* h)
   h->graph_len = 0;
 }
 
+double now_s()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
 int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
 {
+  const bool trace = getenv("LBM_B200_TRACE") != nullptr;
+  const double t0 = now_s();
   CUDA_TRY(cudaSetDevice(s.device));
   s.plane = (size_t)(s.rows + 2) * h->nx;
   const size_t bytes = 9 * s.plane * sizeof(float);
@@ -225,6 +235,7 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   CUDA_TRY(cudaEventCreate(&s.ev_start));
   CUDA_TRY(cudaEventCreate(&s.ev_stop));
 
+  const double t1 = now_s();
   // obstacle rows: upload the reference's int-per-cell array into the (still unused) second population
   // buffer and bit-pack it on the device: 32 cells per word, rows padded to whole words
   const size_t words = (size_t)s.rows * h->mask_row_words;
@@ -239,6 +250,8 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
     CUDA_TRY(cudaGetLastError());
   }
 
+  if (trace) cudaStreamSynchronize(s.stream);
+  const double t2 = now_s();
   // uniform initial state in both buffers, halo rows included (d2q9-bgk.c:880-902)
   const float w0 = h->density * 4.0f / 9.0f, w1 = h->density / 9.0f, w2 = h->density / 36.0f;
   const unsigned blocks = (unsigned)((s.plane + 255) / 256);
@@ -246,6 +259,9 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(s.stream));
 
+  if (trace)
+    fprintf(stderr, "lbm_b200 trace: slab rows=%d alloc %.3f s, obstacle upload+pack %.3f s, fill %.3f s\n", s.rows,
+            t1 - t0, t2 - t1, now_s() - t2);
   const int accel_global = h->ny - 2;
   s.accel_row = (accel_global >= s.first_row && accel_global < s.first_row + s.rows) ? accel_global - s.first_row + 1 : -1;
   return LBM_B200_OK;

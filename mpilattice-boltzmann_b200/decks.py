@@ -1,6 +1,6 @@
 """Input decks and output files in the reference's formats (Python mirror of the C host).
 
-The product CLI (host/d2q9-bgk.c) does its own parsing and writing in C; this module mirrors
+The product CLI (host/lbm_cli.c) does its own parsing and writing in C; this module mirrors
 the same contract for the Python-side tests and bench:
 
 * ``.params``   -- 7 values ``nx ny maxIters reynolds_dim density accel omega``
