@@ -64,6 +64,7 @@ struct Slab {
   float* av_dev = nullptr;
   size_t av_cap = 0;
   unsigned* cursor = nullptr;
+  unsigned long long* blocked_dev = nullptr;   // blocked cells of this slab, counted while packing the mask
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -190,6 +191,11 @@ void plan(lbm_b200* h)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
       s.per_step = s.grid_full;
+    } else if (use_vec4(h)) {
+      // one launch per step and slab: edge rows first, then the interior (csrc/lbm_kernels.cuh)
+      plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
+      s.grid_edge = s.grid_int = 0;
+      s.per_step = s.grid_full;
     } else {
       plan_region(h, s.device, 2, &s.threads_edge, &s.grid_edge);
       plan_region(h, s.device, s.rows - 2, &s.threads_int, &s.grid_int);
@@ -246,7 +252,9 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   {
     const long warps = (long)s.rows * ((h->mask_row_words + 31) / 32);
     const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-    lbm::pack_mask<<<blocks, 256, 0, s.stream>>>(staged, h->nx, s.rows, h->mask_row_words, s.mask);
+    CUDA_TRY(cudaMalloc(&s.blocked_dev, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(s.blocked_dev, 0, sizeof(unsigned long long), s.stream));
+    lbm::pack_mask<<<blocks, 256, 0, s.stream>>>(staged, h->nx, s.rows, h->mask_row_words, s.mask, s.blocked_dev);
     CUDA_TRY(cudaGetLastError());
   }
 
@@ -308,6 +316,21 @@ StepArgs base_args(const lbm_b200* h, const Slab& s, int slot, bool fold_accel)
   return a;
 }
 
+// halo wiring of a slab's step: where the outgoing rows go and which flag words order the exchange
+void peer_args(const lbm_b200* h, const Slab& s, StepArgs& a)
+{
+  a.south_of_first = 0;
+  a.north_of_last = s.rows + 1;
+  a.north_dst = s.north.buf[h->cur ^ 1]; a.north_plane = s.north.plane; a.north_row = 0;
+  a.south_dst = s.south.buf[h->cur ^ 1]; a.south_plane = s.south.plane; a.south_row = s.south.rows + 1;
+  a.wait_from_south = s.flags + kFromSouth;
+  a.wait_from_north = s.flags + kFromNorth;
+  a.signal_north = s.north.flags + kFromSouth;     // I am my northern neighbour's south
+  a.signal_south = s.south.flags + kFromNorth;
+  a.epoch = s.flags + kEpoch;
+  a.done = s.flags + kDone;
+}
+
 template <bool PEER>
 int launch_step(lbm_b200* h, const Slab& s, const StepArgs& a, int grid, int threads)
 {
@@ -345,23 +368,25 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
     a.north_of_last = 1;
     int rc = launch_step<false>(h, s, a, s.grid_full, s.threads_full);
     if (rc) return rc;
+  } else if (use_vec4(h)) {
+    // ONE launch per slab: its first work items are the two edge rows, which wait for the neighbours'
+    // previous halo rows, push this state's halo rows over NVLink and signal; the interior follows in the
+    // same launch while the neighbours consume (replaces MPI_Startall ... interior ... MPI_Waitall, 326-366)
+    for (Slab& s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      StepArgs a = base_args(h, s, slot, fold_accel);
+      a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+      peer_args(h, s, a);
+      int rc = launch_step<true>(h, s, a, s.grid_full, s.threads_full);
+      if (rc) return rc;
+    }
   } else {
-    // edge rows first: they wait for the neighbours' previous edge rows, push this state's
-    // halo rows over NVLink and signal; the interior then runs while the neighbours consume.
+    // scalar kernel: edge rows in their own launch (CTA-level handshake), then the interior
     for (Slab& s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
       StepArgs a = base_args(h, s, slot, fold_accel);
       a.row_begin = 1; a.row_count = 2; a.row_stride = s.rows - 1;
-      a.south_of_first = 0;
-      a.north_of_last = s.rows + 1;
-      a.north_dst = s.north.buf[h->cur ^ 1]; a.north_plane = s.north.plane; a.north_row = 0;
-      a.south_dst = s.south.buf[h->cur ^ 1]; a.south_plane = s.south.plane; a.south_row = s.south.rows + 1;
-      a.wait_from_south = s.flags + kFromSouth;
-      a.wait_from_north = s.flags + kFromNorth;
-      a.signal_north = s.north.flags + kFromSouth;   // I am my northern neighbour's south
-      a.signal_south = s.south.flags + kFromNorth;
-      a.epoch = s.flags + kEpoch;
-      a.done = s.flags + kDone;
+      peer_args(h, s, a);
       int rc = launch_step<true>(h, s, a, s.grid_edge, s.threads_edge);
       if (rc) return rc;
     }
@@ -520,7 +545,7 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
   cudaGetDeviceCount(&ndev);
 
   lbm_b200* h = new lbm_b200();
-  init_common(h, nx, ny, density, accel, omega, lbm_b200_free_cells_inv(obstacles, (long)nx * ny));
+  init_common(h, nx, ny, density, accel, omega, 0.0f);   // free_cells_inv follows from the device-side count below
   h->n_ranks = n_slabs;
   h->slabs.resize(n_slabs);
   for (int i = 0; i < n_slabs; i++) {
@@ -549,6 +574,20 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
   for (int i = 0; i < n_slabs; i++) {
     rc = alloc_slab(h, h->slabs[i], obstacles + (size_t)first[i] * nx);
     if (rc) { lbm_b200_destroy(h); return rc; }
+  }
+  // 1/free cells (d2q9-bgk.c:945-950) from the blocked-cell counts the packing kernels produced
+  {
+    long blocked = 0;
+    for (Slab& s : h->slabs) {
+      unsigned long long n = 0;
+      cudaSetDevice(s.device);
+      if (cudaMemcpy(&n, s.blocked_dev, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        lbm_b200_destroy(h);
+        return fail(LBM_B200_ERR_CUDA, "reading the blocked-cell count failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+      blocked += (long)n;
+    }
+    h->inv = 1.0f / ((long)nx * ny - blocked);
   }
   // ring wiring: direct peer pointers (d2q9-bgk.c:244-247 for the neighbour ranks)
   if (n_slabs > 1) {
@@ -925,8 +964,8 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "cache_hint")) *value = h->opt_cache_hint;
   else if (!strcmp(key, "resident")) *value = h->resident ? 1 : 0;
   else if (!strcmp(key, "grid")) *value = h->slabs[0].per_step;
-  else if (!strcmp(key, "threads")) *value = h->n_ranks == 1 ? h->slabs[0].threads_full : h->slabs[0].threads_int;
-  else if (!strcmp(key, "launches_per_step")) *value = h->n_ranks == 1 ? 1 : 2;
+  else if (!strcmp(key, "threads")) *value = h->slabs[0].grid_full ? h->slabs[0].threads_full : h->slabs[0].threads_int;
+  else if (!strcmp(key, "launches_per_step")) *value = (h->n_ranks == 1 || use_vec4(h)) ? 1 : 2;
   else if (!strcmp(key, "launches")) *value = h->launches;
   else return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);
   return LBM_B200_OK;
@@ -956,6 +995,7 @@ void lbm_b200_destroy(lbm_b200* h)
     if (s.partials) cudaFree(s.partials);
     if (s.av_dev) cudaFree(s.av_dev);
     if (s.cursor) cudaFree(s.cursor);
+    if (s.blocked_dev) cudaFree(s.blocked_dev);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
   }

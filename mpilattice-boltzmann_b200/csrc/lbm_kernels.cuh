@@ -84,6 +84,35 @@ __device__ __forceinline__ void peer_signal(const StepArgs& a)
   }
 }
 
+// Warp-granular versions for the 128-bit kernel, where the edge-row segments are the first work items of
+// the SAME launch as the interior: only the warps that own an edge segment wait, and the warp that
+// completes the last of the `total` edge segments publishes the epoch.
+__device__ __forceinline__ void warp_peer_wait(const StepArgs& a)
+{
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
+    while ((int)(ld_acquire_sys(a.wait_from_south) - need) < 0) __nanosleep(20);
+    while ((int)(ld_acquire_sys(a.wait_from_north) - need) < 0) __nanosleep(20);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_peer_signal(const StepArgs& a, unsigned total)
+{
+  __threadfence_system();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned prev = atomicAdd(a.done, 1u);
+    if (prev == total - 1) {
+      *a.done = 0;
+      __threadfence_system();
+      const unsigned next = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
+      st_release_sys(a.signal_north, next);
+      st_release_sys(a.signal_south, next);
+      *reinterpret_cast<volatile unsigned*>(a.epoch) = next;
+    }
+  }
+}
+
 // Global access flavours of the vec4 kernel (template parameter HINT):
 //   0  ld.global.nc (read-only path) + plain st.global
 //   1  ld.global.cs + st.global.cs   (streaming: evict-first in L1 and L2)
@@ -133,7 +162,7 @@ __device__ __forceinline__ void block_sum_to(double v, double* out)
 // access is a 128-bit aligned, fully coalesced row load/store; the +-1 x-shifts of the six
 // x-moving populations come from the neighbouring lane by warp shuffle, and only the two end
 // lanes of a segment fetch one extra scalar across the segment (or the periodic) boundary.
-// Persistent grid: CTAs stride over the segments.  Requires nx % 4 == 0, nx >= 8.
+// CTAs stride over the segments (grid sized by the host).  Requires nx % 4 == 0, nx >= 8.
 // ---------------------------------------------------------------------------------------
 // One pass of this CTA over its share of the row segments: src -> dst.  Returns the thread's share of
 // Sigma |m|/rho.  `accel_row` = padded row that gets the next step's body force folded in (or -1).
@@ -148,9 +177,29 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
   double acc = 0.0;
 
   for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
-    const int ri = (int)(seg / a.chunks);
-    const int ch = (int)(seg - (long)ri * a.chunks);
-    const int row = a.row_begin + ri * a.row_stride;
+    int row, ch;
+    bool edge = false;
+    if (PEER) {
+      // multi-GPU: the two edge rows are the first 2*chunks work items, so their halo stores leave over
+      // NVLink at the start of the launch and the interior hides the exchange (d2q9-bgk.c:326-366)
+      const long e2 = 2L * a.chunks;
+      if (seg < e2) {
+        edge = true;
+        const bool first = seg < a.chunks;
+        row = first ? a.row_first : a.row_last;
+        ch = (int)(first ? seg : seg - a.chunks);
+        warp_peer_wait(a);
+      } else {
+        const long s2 = seg - e2;
+        const int ri = (int)(s2 / a.chunks);
+        ch = (int)(s2 - (long)ri * a.chunks);
+        row = a.row_first + 1 + ri;
+      }
+    } else {
+      const int ri = (int)(seg / a.chunks);
+      ch = (int)(seg - (long)ri * a.chunks);
+      row = a.row_begin + ri * a.row_stride;
+    }
     const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
     const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
     const int x0 = ch * kSegCells + lane * 4;
@@ -243,18 +292,20 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
         }
       }
     }
+    if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
   }
 
   return acc;
 }
 
+// PEER = true: a slab of a multi-GPU ring -- ONE launch per timestep computes the whole slab, pushes the
+// outgoing halo rows into the neighbours' buffers and does the flag handshake (loads are L2-coherent
+// ld.global.cg, HINT 3, because halo rows are written by another GPU).
 template <bool PEER, int MIN_CTAS, int HINT>
 __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 {
-  if (PEER) peer_wait(a);
-  const double acc = vec4_pass<PEER, HINT>(a, a.src, a.dst, a.accel_row);
+  const double acc = vec4_pass<PEER, PEER ? 3 : HINT>(a, a.src, a.dst, a.accel_row);
   block_sum_to(acc, a.partials + blockIdx.x);
-  if (PEER) peer_signal(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -395,7 +446,8 @@ __global__ void advance_cursor(unsigned* cursor, unsigned by) { *cursor += by; }
 
 // int-per-cell obstacle rows (the reference's layout, d2q9-bgk.c:875) -> 1 bit per cell.  One warp packs
 // 32 words of one row at a time: coalesced 128 B reads, one ballot per word.
-__global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words, uint32_t* mask)
+__global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words, uint32_t* mask,
+                          unsigned long long* blocked_cells)
 {
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -411,6 +463,11 @@ __global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words,
     if (i == lane) mine = word;
   }
   if (w0 + lane < row_words) mask[(size_t)r * row_words + w0 + lane] = mine;
+  // number of blocked cells (for free_cells_inv, d2q9-bgk.c:945-950): one atomic per warp
+  unsigned n = __popc(mine);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0 && n) atomicAdd(blocked_cells, (unsigned long long)n);
 }
 
 // uniform initial state, every padded row (d2q9-bgk.c:880-902)
