@@ -166,13 +166,26 @@ def test_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny):
     obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
     cells0 = random_cells(rng, ny, nx)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
-        assert sim.get_option("launches_per_step") == 2
+        assert sim.get_option("launches_per_step") == 1      # edge rows + halo push + interior in ONE launch per slab
         sim.set_cells(cells0)
         ref = assert_parity(sim, oracle, pkg, cells0, obstacles, 21)
         ux, uy, u, pr = sim.final_state()
         rux, ruy, ru, rpr = oracle.final_state(ref, obstacles, DENSITY)
         for got, want in ((ux, rux), (uy, ruy), (u, ru), (pr, rpr)):
             assert np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("n_slabs,nx,ny", [(2, 30, 16), (3, 128, 19)])
+def test_slabs_with_the_scalar_kernel(pkg, oracle, n_slabs, nx, ny):
+    """nx not a multiple of 4 (or kernel 1 forced): edge rows in their own launch with a CTA-level handshake."""
+    rng = np.random.default_rng(n_slabs * 31 + nx)
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        sim.set_option("kernel", 1)
+        assert sim.get_option("launches_per_step") == 2
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 23)
 
 
 def test_final_state_fields_bit_exact(pkg, oracle):
