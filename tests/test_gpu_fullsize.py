@@ -56,3 +56,26 @@ def test_plain_channel_is_x_invariant_and_matches_an_8_wide_oracle(pkg, oracle):
         pressure = sim.final_state()[3]
     assert np.array_equal(bits(pressure), bits(np.repeat(ref_pressure[:, :1], NX, axis=1)))
     assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
+
+
+def test_synthetic_deck_through_the_cli(pkg, oracle, tmp_path):
+    """BASELINE.json configs[4] end to end: generated 16384 x 16384 channel deck (32768 obstacle lines) through
+    the drop-in command line, final_state.dat switched off (it would be ~23 GB of text)."""
+    import os
+    import subprocess
+    iters = 12
+    pfile, ofile = pkg.decks.write_channel_deck(str(tmp_path), NX, NY, iters, density=DENSITY, accel=ACCEL, omega=OMEGA)
+    res = subprocess.run([pkg.EXE_PATH, pfile, ofile], cwd=tmp_path, capture_output=True, text=True,
+                         env={**os.environ, "LBM_FINAL_STATE": "0", "LBM_VERBOSE": "1"})
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.splitlines()[0] == "==done==" and not os.path.exists(tmp_path / "final_state.dat")
+    av = pkg.decks.read_av_vels(str(tmp_path / "av_vels.dat"))
+    narrow = pkg.decks.channel_obstacles(8, NY)
+    cells = oracle.init_cells(8, NY, DENSITY)
+    _, av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow), exact=True)
+    assert av.shape == av_ref.shape and np.max(np.abs(av - av_ref) / av_ref) < 2e-6
+    # Reynolds number printed from the final state: same value as the 8-wide oracle's (x-invariant flow), to fp32
+    # summation noise of the 268 M-term sequential sum the reference prescribes
+    reynolds = float(res.stdout.splitlines()[1].split()[-1])
+    ref_re = float(oracle.reynolds(cells, narrow, pkg.free_cells_inv(narrow), OMEGA, 10))
+    assert abs(reynolds - ref_re) / ref_re < 5e-2
