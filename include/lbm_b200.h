@@ -144,7 +144,8 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
  *   "ctas_per_sm"   persistent-grid size in CTAs per SM (0 = occupancy query)
  *   "min_ctas"      register budget of the 128-bit kernel: 2, 3 or 4 resident CTAs per SM
  *   "cache_hint"    0 = read-only loads + plain stores, 1 = streaming loads and stores,
- *                   2 = read-only loads + streaming stores
+ *                   2 = read-only loads + streaming stores, 4 = as 0 plus a bulk L2 prefetch of each
+ *                   warp's next row segment
  */
 int lbm_b200_set_option(lbm_b200* handle, const char* key, long value);
 int lbm_b200_get_option(const lbm_b200* handle, const char* key, long* value);

@@ -342,6 +342,7 @@ int launch_step(lbm_b200* h, const Slab& s, const StepArgs& a, int grid, int thr
   do {                                                                                         \
     if (h->opt_cache_hint == 1) LBM_LAUNCH_VEC4(M, 1);                                         \
     else if (h->opt_cache_hint == 2) LBM_LAUNCH_VEC4(M, 2);                                    \
+    else if (h->opt_cache_hint == 4) LBM_LAUNCH_VEC4(M, 4);                                    \
     else LBM_LAUNCH_VEC4(M, 0);                                                                \
   } while (0)
     if (h->opt_min_ctas >= 4) LBM_LAUNCH_HINT(4);
@@ -943,7 +944,7 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "resident must be -1, 0 or 1");
     h->opt_resident = value;
   } else if (!strcmp(key, "cache_hint")) {
-    if (value < 0 || value > 2) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1 or 2");
+    if (value < 0 || value > 4 || value == 3) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1, 2 or 4");
     h->opt_cache_hint = value;
   } else {
     return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);

@@ -118,6 +118,7 @@ __device__ __forceinline__ void warp_peer_signal(const StepArgs& a, unsigned tot
 //   1  ld.global.cs + st.global.cs   (streaming: evict-first in L1 and L2)
 //   2  ld.global.nc + st.global.cs
 //   3  ld.global.cg (L2 only, coherent within a launch) + plain st.global   [resident kernel]
+//   4  as 0, plus a bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the warp's NEXT segment
 template <int HINT>
 __device__ __forceinline__ float4 load4(const float* p)
 {
@@ -135,7 +136,7 @@ __device__ __forceinline__ float load1(const float* p)
 template <int HINT>
 __device__ __forceinline__ void store4(float* p, float4 v)
 {
-  if (HINT == 0 || HINT == 3) *reinterpret_cast<float4*>(p) = v;
+  if (HINT == 0 || HINT == 3 || HINT == 4) *reinterpret_cast<float4*>(p) = v;
   else __stcs(reinterpret_cast<float4*>(p), v);
 }
 
@@ -210,6 +211,24 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
     const int xe = (x0 + 4 >= a.nx) ? 0 : x0 + 4;
 
     const size_t o_c = (size_t)row * a.nx, o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
+
+    if (HINT == 4 && !PEER) {
+      // pull the nine 512-byte row pieces of this warp's next segment into L2 while this one is processed:
+      // lane k asks for plane k with one bulk-prefetch instruction
+      const long nxt = seg + (long)gridDim.x * warps;
+      if (nxt < nseg && lane < 9) {
+        const int nri = (int)(nxt / a.chunks);
+        const int nch = (int)(nxt - (long)nri * a.chunks);
+        const int nrow = a.row_begin + nri * a.row_stride;
+        const int nrs = (nrow == a.row_first) ? a.south_of_first : nrow - 1;
+        const int nrn = (nrow == a.row_last) ? a.north_of_last : nrow + 1;
+        // planes 0,1,3 come from the row itself, 2,5,6 from the row below, 4,7,8 from the row above
+        const int from = (lane == 0 || lane == 1 || lane == 3) ? nrow : ((lane == 2 || lane == 5 || lane == 6) ? nrs : nrn);
+        const float* p = src + (size_t)lane * P + (size_t)from * a.nx + (size_t)nch * kSegCells;
+        const unsigned bytes = (unsigned)min(kSegCells, a.nx - nch * kSegCells) * 4u;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+      }
+    }
 
     float4 c[9];
     float e_c = 0.f, e_s = 0.f, e_n = 0.f;

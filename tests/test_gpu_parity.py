@@ -104,7 +104,7 @@ def test_runs_compose(pkg, oracle):
         assert_av(av, ref_av, ref_exact)
 
 
-@pytest.mark.parametrize("min_ctas,ctas_per_sm,hint", [(2, 0, 0), (3, 0, 1), (2, 1, 2), (4, 7, 0)])
+@pytest.mark.parametrize("min_ctas,ctas_per_sm,hint", [(2, 0, 0), (3, 0, 1), (2, 1, 2), (4, 7, 0), (2, 3, 4), (2, 0, 4)])
 def test_launch_geometry_does_not_change_results(pkg, oracle, min_ctas, ctas_per_sm, hint):
     rng = np.random.default_rng(11)
     nx, ny = 1024, 40
