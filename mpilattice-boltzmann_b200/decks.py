@@ -165,3 +165,32 @@ def write_channel_deck(directory: str, nx: int, ny: int, max_iters: int, *, reyn
         for y in (0, ny - 1):
             fh.write("".join(f"{x} {y} 1\n" for x in range(nx)))
     return pfile, ofile
+
+
+def cylinder_array_obstacles(nx: int, ny: int, pitch: int = 64, radius: int = 12) -> np.ndarray:
+    """A richer synthetic deck: the channel walls plus a staggered array of solid discs of
+    `radius` every `pitch` cells.  Periodic in x with period 2*pitch when nx is a multiple of it."""
+    obstacles = channel_obstacles(nx, ny)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    row = yy // pitch
+    cx = (xx + (row % 2) * (pitch // 2)) % pitch - pitch // 2
+    cy = yy % pitch - pitch // 2
+    inside = (cx * cx + cy * cy <= radius * radius) & (yy > pitch // 2) & (yy < ny - pitch // 2)
+    obstacles[inside] = 1
+    obstacles[ny - 2, :] = 0            # keep the driven row open
+    return obstacles
+
+
+def write_obstacle_deck(directory: str, name: str, obstacles: np.ndarray, max_iters: int, *, reynolds_dim=10,
+                        density=0.1, accel=0.005, omega=1.85):
+    """Writes ``input_<name>.params`` / ``obstacles_<name>.dat`` for an arbitrary obstacle map."""
+    os.makedirs(directory, exist_ok=True)
+    ny, nx = obstacles.shape
+    pfile = os.path.join(directory, f"input_{name}.params")
+    ofile = os.path.join(directory, f"obstacles_{name}.dat")
+    with open(pfile, "w") as fh:
+        fh.write(f"{nx}\n{ny}\n{max_iters}\n{reynolds_dim}\n{density}\n{accel}\n{omega}\n")
+    ys, xs = np.nonzero(obstacles)
+    with open(ofile, "w") as fh:
+        fh.write("".join(f"{x} {y} 1\n" for x, y in zip(xs.tolist(), ys.tolist())))
+    return pfile, ofile

@@ -81,3 +81,14 @@ def test_synthetic_channel_deck(pkg, tmp_path):
     ob, free = pkg.decks.read_obstacles(ofile, p.nx, p.ny)
     assert (p.nx, p.ny, p.max_iters) == (64, 32, 10)
     assert free == 64 * 30 and np.array_equal(ob, pkg.decks.channel_obstacles(64, 32))
+
+
+def test_cylinder_array_deck_round_trips(pkg, tmp_path):
+    ob = pkg.decks.cylinder_array_obstacles(256, 192)
+    assert ob[0].all() and ob[-1].all() and not ob[-2].any()
+    assert 0.05 < ob.mean() < 0.3
+    assert np.array_equal(ob[:, :128], ob[:, 128:])               # periodic in x with period 2*pitch
+    pfile, ofile = pkg.decks.write_obstacle_deck(str(tmp_path), "cyl", ob, 7)
+    p = pkg.decks.read_params(pfile)
+    back, free = pkg.decks.read_obstacles(ofile, p.nx, p.ny)
+    assert np.array_equal(back, ob) and free == ob.size - int(ob.sum()) and p.max_iters == 7

@@ -15,6 +15,22 @@ NX = NY = 16384
 DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
 
 
+def test_full_size_cylinder_array(pkg, oracle):
+    """16384 x 16384 cylinder-array deck (period 128 in x) against the tiled 128-wide oracle, bit for bit."""
+    period, iters = 128, 5
+    narrow = pkg.decks.cylinder_array_obstacles(period, NY)
+    cells = oracle.init_cells(period, NY, DENSITY)
+    _, av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow), exact=True)
+    ref_pressure = oracle.final_state(cells, narrow, DENSITY)[3]
+    obstacles = pkg.decks.cylinder_array_obstacles(NX, NY)
+    assert np.array_equal(obstacles, np.tile(narrow, (1, NX // period)))
+    with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        av = sim.run(iters)
+        pressure = sim.final_state()[3]
+    assert np.array_equal(bits(pressure), bits(np.tile(ref_pressure, (1, NX // period))))
+    assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
+
+
 def narrow_pattern(period, rng):
     ob = (rng.random((NY, period)) < 0.02).astype(np.int32)
     ob[0, :] = ob[-1, :] = 1                     # the synthetic deck's channel walls (SURVEY 8d)

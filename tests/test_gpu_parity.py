@@ -223,3 +223,12 @@ def test_total_density_is_conserved_on_device(pkg, oracle):
         sim.run(400)
         after = oracle.total_density(sim.get_cells())
     assert abs(after - before) / before < 1e-5
+
+
+def test_cylinder_array_deck(pkg, oracle):
+    """The richer synthetic deck (discs in a channel): many obstacle edges at every alignment within a segment."""
+    nx, ny = 512, 192
+    obstacles = pkg.decks.cylinder_array_obstacles(nx, ny)
+    cells0 = oracle.init_cells(nx, ny, DENSITY)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        assert_parity(sim, oracle, pkg, cells0, obstacles, 60)
