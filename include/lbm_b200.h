@@ -73,6 +73,15 @@ int lbm_b200_device_count(void);
 int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                     const int* obstacles, int n_slabs, const int* devices);
 
+/* As lbm_b200_create with one slab on `device`, but with ONE population buffer instead of the reference's
+ * cells/tmp_cells pair (d2q9-bgk.c:865-872, swapped at 376-378): the timestep streams in place (the "AA"
+ * access pattern: steps alternate between a neighbour-access and a cell-local flavour, csrc/lbm_kernels.cuh
+ * kernel 4).  Half the device memory per cell (36 B + 1 bit), the same 72 B/cell/step of traffic and
+ * bit-identical results; state in/out is staged through a bounded 256 MB buffer.  Requires nx % 4 == 0,
+ * nx >= 8.  Single device only. */
+int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                            const int* obstacles, int device);
+
 /* ---- one slab per process (one rank per GPU; ranks launched by torchrun or similar) --- */
 
 /* As lbm_b200_create, for the slab [first_row, first_row + rows) of a ny_global-row grid owned
@@ -135,7 +144,10 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
 
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
  *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit); reads back 3
- *                   when the resident variant of kernel 2 is in use
+ *                   when the resident variant of kernel 2 is in use and 4 on an in-place handle
+ *   "inplace"       read-only: 1 on a handle made by lbm_b200_create_inplace
+ *   "staging_bytes" in-place handles: size of the device staging buffer that get_cells / set_cells /
+ *                   get_final_state move the state through, in chunks of whole rows (default 256 MB)
  *   "resident"      1 = run up to 256 timesteps per cooperative launch with a grid-wide barrier between
  *                   steps (for launch-latency-bound grids), 0 = never, -1 = automatic (single-GPU grids of
  *                   up to 2^22 cells)
@@ -145,7 +157,8 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
  *   "min_ctas"      register budget of the 128-bit kernel: 2, 3 or 4 resident CTAs per SM
  *   "cache_hint"    0 = read-only loads + plain stores, 1 = streaming loads and stores,
  *                   2 = read-only loads + streaming stores, 4 = as 0 plus a bulk L2 prefetch of each
- *                   warp's next row segment
+ *                   warp's next row segment.  In-place handles: 0 = L2-only loads (ld.global.cg) + plain
+ *                   stores, 1 = streaming loads and stores, 2 = plain (L1-cached) loads + plain stores
  */
 int lbm_b200_set_option(lbm_b200* handle, const char* key, long value);
 int lbm_b200_get_option(const lbm_b200* handle, const char* key, long* value);

@@ -65,6 +65,8 @@ struct Slab {
   size_t av_cap = 0;
   unsigned* cursor = nullptr;
   unsigned long long* blocked_dev = nullptr;   // blocked cells of this slab, counted while packing the mask
+  float* bounce = nullptr;              // in-place handles: bounded staging buffer for state in/out
+  size_t bounce_bytes = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -91,6 +93,7 @@ constexpr int kMaxCtasPerSm = 128;      // upper bound of the oversubscribed gri
 constexpr long kResidentAutoMinCells = 1L << 18;
 constexpr long kGraphAutoCells = 1L << 22;  // up to 2048^2: step kernel <= ~60 us, launch gaps matter
 constexpr int kChunkSteps = 256;        // steps whose CTA partials are kept before one reduce launch
+constexpr size_t kBounceBytes = 256u << 20;   // staging buffer of in-place handles (state in/out goes through it in row chunks)
 
 }  // namespace
 
@@ -103,9 +106,12 @@ struct lbm_b200 {
   int rank0 = 0;                        // ring index of slabs[0]
   bool multi_process = false;
   bool connected = true;
-  int cur = 0;                          // index of the buffer holding the current state
+  bool inplace = false;                 // ONE population buffer, AA access pattern (csrc/lbm_kernels.cuh, kernel 4)
+  int cur = 0;                          // index of the buffer holding the current state; in-place handles: the
+                                        // layout of buf[0] (0 = canonical L0, 1 = L1 after an odd number of steps)
   std::vector<Slab> slabs;
   // options
+  long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   int last_iters = 0;
@@ -149,7 +155,8 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
       const int fit = occupancy(lbm::steps_resident<2>, *threads);
       per_sm = per_sm > 0 ? std::min(per_sm, fit) : fit;
     } else if (per_sm <= 0) {
-      per_sm = (h->opt_min_ctas >= 4)   ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
+      per_sm = h->inplace               ? occupancy(lbm::step_inplace<true, 0>, *threads)
+               : (h->opt_min_ctas >= 4) ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
                : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
                                         : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
       // Oversubscribe the resident slots so the hardware CTA scheduler balances the two dies, but keep
@@ -173,7 +180,7 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
 // The resident kernel pays off where a step is only a few microseconds of work (launch latency bound).
 bool want_resident(const lbm_b200* h)
 {
-  if (h->opt_resident == 0 || h->n_ranks != 1 || h->slabs.size() != 1 || !use_vec4(h)) return false;
+  if (h->opt_resident == 0 || h->n_ranks != 1 || h->slabs.size() != 1 || !use_vec4(h) || h->inplace) return false;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->slabs[0].device);
   if (!coop) return false;
@@ -229,7 +236,7 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   CUDA_TRY(cudaSetDevice(s.device));
   s.plane = (size_t)(s.rows + 2) * h->nx;
   const size_t bytes = 9 * s.plane * sizeof(float);
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < (h->inplace ? 1 : 2); b++) {
     cudaError_t e = cudaMalloc(&s.buf[b], bytes);
     if (e != cudaSuccess)
       return fail(LBM_B200_ERR_ALLOC, "cudaMalloc of %zu bytes for populations failed: %s", bytes, cudaGetErrorString(e));
@@ -247,7 +254,7 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   const size_t words = (size_t)s.rows * h->mask_row_words;
   const size_t cells = (size_t)s.rows * h->nx;
   CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
-  int* staged = reinterpret_cast<int*>(s.buf[1]);
+  int* staged = reinterpret_cast<int*>(s.buf[h->inplace ? 0 : 1]);   // 4 of the buffer's 36 bytes per cell
   CUDA_TRY(cudaMemcpyAsync(staged, obstacles_rows, cells * sizeof(int), cudaMemcpyHostToDevice, s.stream));
   {
     const long warps = (long)s.rows * ((h->mask_row_words + 31) / 32);
@@ -263,7 +270,7 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   // uniform initial state in both buffers, halo rows included (d2q9-bgk.c:880-902)
   const float w0 = h->density * 4.0f / 9.0f, w1 = h->density / 9.0f, w2 = h->density / 36.0f;
   const unsigned blocks = (unsigned)((s.plane + 255) / 256);
-  for (int b = 0; b < 2; b++) lbm::fill_planes<<<blocks, 256, 0, s.stream>>>(s.buf[b], s.plane, w0, w1, w2);
+  for (int b = 0; b < (h->inplace ? 1 : 2); b++) lbm::fill_planes<<<blocks, 256, 0, s.stream>>>(s.buf[b], s.plane, w0, w1, w2);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(s.stream));
 
@@ -298,11 +305,39 @@ int ensure_partials(lbm_b200* h)
   return LBM_B200_OK;
 }
 
+// where the canonical populations of the current state live (see lbm::locate)
+lbm::Layout layout_of(const lbm_b200* h, const Slab& s)
+{
+  return lbm::Layout{s.plane, h->nx, s.rows, h->inplace ? h->cur : 0};
+}
+
+// Device staging for state in/out: the idle ping-pong buffer, or (in-place handles, which have none) a
+// bounded bounce buffer.  *rows = how many grid rows of `row_bytes` fit.
+int staging(lbm_b200* h, Slab& s, size_t row_bytes, int rows_wanted, float** ptr, int* rows)
+{
+  if (!h->inplace) {
+    *ptr = s.buf[h->cur ^ 1];
+    *rows = rows_wanted;                 // 9 planes of rows+2 rows always hold what the callers ask for
+    return LBM_B200_OK;
+  }
+  const size_t want = std::min(std::max((size_t)h->opt_staging_bytes, row_bytes), row_bytes * (size_t)rows_wanted);
+  if (s.bounce_bytes < want || s.bounce_bytes > std::max(want, (size_t)h->opt_staging_bytes)) {
+    if (s.bounce) CUDA_TRY(cudaFree(s.bounce));
+    s.bounce = nullptr; s.bounce_bytes = 0;
+    cudaError_t e = cudaMalloc(&s.bounce, want);
+    if (e != cudaSuccess) return fail(LBM_B200_ERR_ALLOC, "cudaMalloc of %zu bytes of staging failed: %s", want, cudaGetErrorString(e));
+    s.bounce_bytes = want;
+  }
+  *ptr = s.bounce;
+  *rows = (int)std::min<size_t>((size_t)rows_wanted, s.bounce_bytes / row_bytes);
+  return LBM_B200_OK;
+}
+
 StepArgs base_args(const lbm_b200* h, const Slab& s, int slot, bool fold_accel)
 {
   StepArgs a{};
-  a.src = s.buf[h->cur];
-  a.dst = s.buf[h->cur ^ 1];
+  a.src = s.buf[h->inplace ? 0 : h->cur];
+  a.dst = s.buf[h->inplace ? 0 : h->cur ^ 1];
   a.plane = s.plane;
   a.mask = s.mask;
   a.mask_row_words = h->mask_row_words;
@@ -360,7 +395,26 @@ int launch_step(lbm_b200* h, const Slab& s, const StepArgs& a, int grid, int thr
 // One timestep on every slab of this handle: d2q9-bgk.c:326-378.
 int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
 {
-  if (h->n_ranks == 1) {
+  if (h->inplace) {
+    // one buffer: the NEIGHBOUR flavour takes layout L0 to L1, the LOCAL flavour takes it back
+    Slab& s = h->slabs[0];
+    CUDA_TRY(cudaSetDevice(s.device));
+    StepArgs a = base_args(h, s, slot, fold_accel);
+    a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+    a.south_of_first = s.rows;
+    a.north_of_last = 1;
+    h->launches++;
+#define LBM_LAUNCH_INPLACE(H)                                                                      \
+  do {                                                                                             \
+    if (h->cur == 0) lbm::step_inplace<true, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);  \
+    else lbm::step_inplace<false, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);             \
+  } while (0)
+    if (h->opt_cache_hint == 1) LBM_LAUNCH_INPLACE(1);
+    else if (h->opt_cache_hint == 2) LBM_LAUNCH_INPLACE(2);
+    else LBM_LAUNCH_INPLACE(0);
+#undef LBM_LAUNCH_INPLACE
+    CUDA_TRY(cudaGetLastError());
+  } else if (h->n_ranks == 1) {
     Slab& s = h->slabs[0];
     CUDA_TRY(cudaSetDevice(s.device));
     StepArgs a = base_args(h, s, slot, fold_accel);
@@ -533,12 +587,14 @@ float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
   return 1.0f / free_cells;
 }
 
-int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
-                    const int* obstacles, int n_slabs, const int* devices)
+static int create_whole(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                        const int* obstacles, int n_slabs, const int* devices, bool inplace)
 {
   int rc = check_common(nx, ny, omega, obstacles, handle);
   if (rc) return rc;
   if (n_slabs < 1) return fail(LBM_B200_ERR_ARG, "n_slabs must be >= 1");
+  if (inplace && !(nx % 4 == 0 && nx >= 8))
+    return fail(LBM_B200_ERR_ARG, "in-place streaming needs nx %% 4 == 0 and nx >= 8 (got %d)", nx);
   std::vector<int> rows(n_slabs), first(n_slabs);
   rc = lbm_b200_decompose(ny, n_slabs, rows.data(), first.data());
   if (rc) return rc;
@@ -547,6 +603,8 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
 
   lbm_b200* h = new lbm_b200();
   init_common(h, nx, ny, density, accel, omega, 0.0f);   // free_cells_inv follows from the device-side count below
+  h->inplace = inplace;
+  if (inplace) { h->opt_kernel = 0; if (h->opt_cache_hint > 2) h->opt_cache_hint = 0; }
   h->n_ranks = n_slabs;
   h->slabs.resize(n_slabs);
   for (int i = 0; i < n_slabs; i++) {
@@ -617,6 +675,18 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
   if (rc) { lbm_b200_destroy(h); return rc; }
   *handle = h;
   return LBM_B200_OK;
+}
+
+int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                    const int* obstacles, int n_slabs, const int* devices)
+{
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, n_slabs, devices, false);
+}
+
+int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                            const int* obstacles, int device)
+{
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, 1, &device, true);
 }
 
 int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
@@ -742,8 +812,8 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       if (s.accel_row < 0) continue;
       CUDA_TRY(cudaSetDevice(s.device));
       lbm::accelerate_row<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
-          s.buf[h->cur], s.plane, s.mask + (size_t)(s.accel_row - 1) * h->mask_row_words, h->nx,
-          (size_t)s.accel_row * h->nx, h->sc.aw1, h->sc.aw2);
+          s.buf[h->inplace ? 0 : h->cur], layout_of(h, s), s.mask + (size_t)(s.accel_row - 1) * h->mask_row_words,
+          s.accel_row, h->sc.aw1, h->sc.aw2);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
     }
@@ -867,14 +937,20 @@ int lbm_b200_get_cells(lbm_b200* h, float* cells)
   size_t done = 0;
   for (Slab& s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    const size_t ncell = (size_t)s.rows * h->nx;
-    float* scratch = s.buf[h->cur ^ 1];
-    const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
-    lbm::soa_to_aos<<<blocks, 256, 0, s.stream>>>(s.buf[h->cur], s.plane, (size_t)h->nx, ncell, scratch);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(cells + done * 9, scratch, ncell * 9 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
-    done += ncell;
+    const size_t row_floats = (size_t)h->nx * 9;
+    float* scratch = nullptr;
+    int step = 0;
+    int rc = staging(h, s, row_floats * sizeof(float), s.rows, &scratch, &step);
+    if (rc) return rc;
+    for (int r = 0; r < s.rows; r += step) {
+      const size_t ncell = (size_t)std::min(step, s.rows - r) * h->nx;
+      const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
+      lbm::soa_to_aos<<<blocks, 256, 0, s.stream>>>(s.buf[h->inplace ? 0 : h->cur], layout_of(h, s), 1 + r, ncell, scratch);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(cells + done * 9, scratch, ncell * 9 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+      done += ncell;
+    }
   }
   return LBM_B200_OK;
 }
@@ -884,20 +960,27 @@ int lbm_b200_set_cells(lbm_b200* h, const float* cells)
   if (!h || !cells) return fail(LBM_B200_ERR_ARG, "NULL argument");
   if (h->multi_process) return fail(LBM_B200_ERR_STATE, "set_cells is not available on multi-process slab handles");
   const size_t row_floats = (size_t)h->nx * 9;
+  if (h->inplace) { lbm_b200_sync(h); h->cur = 0; }   // the canonical layout is written
   for (Slab& s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    float* scratch = s.buf[h->cur ^ 1];
+    float* scratch = nullptr;
+    int step = 0;
+    int rc = staging(h, s, row_floats * sizeof(float), s.rows + 2, &scratch, &step);
+    if (rc) return rc;
     // owned rows plus both halo rows, taken from the periodic global grid
-    for (int r = 0; r < s.rows + 2; r++) {
-      const int gy = ((s.first_row + r - 1) % h->ny + h->ny) % h->ny;
-      CUDA_TRY(cudaMemcpyAsync(scratch + (size_t)r * row_floats, cells + (size_t)gy * row_floats,
-                               row_floats * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    for (int r0 = 0; r0 < s.rows + 2; r0 += step) {
+      const int n = std::min(step, s.rows + 2 - r0);
+      for (int r = r0; r < r0 + n; r++) {
+        const int gy = ((s.first_row + r - 1) % h->ny + h->ny) % h->ny;
+        CUDA_TRY(cudaMemcpyAsync(scratch + (size_t)(r - r0) * row_floats, cells + (size_t)gy * row_floats,
+                                 row_floats * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+      }
+      const size_t ncell = (size_t)n * h->nx;
+      const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
+      lbm::aos_to_soa<<<blocks, 256, 0, s.stream>>>(scratch, s.plane, (size_t)r0 * h->nx, ncell, s.buf[h->inplace ? 0 : h->cur]);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
     }
-    const size_t ncell = (size_t)(s.rows + 2) * h->nx;
-    const unsigned blocks = (unsigned)((ncell * 9 + 255) / 256);
-    lbm::aos_to_soa<<<blocks, 256, 0, s.stream>>>(scratch, s.plane, 0, ncell, s.buf[h->cur]);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
   }
   return LBM_B200_OK;
 }
@@ -909,17 +992,22 @@ int lbm_b200_get_final_state(lbm_b200* h, float* u_x, float* u_y, float* u, floa
   size_t done = 0;
   for (Slab& s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    const size_t ncell = (size_t)s.rows * h->nx;
-    float* scratch = s.buf[h->cur ^ 1];
-    const unsigned blocks = (unsigned)((ncell + 255) / 256);
-    lbm::final_state<<<blocks, 256, 0, s.stream>>>(s.buf[h->cur], s.plane, (size_t)h->nx, s.mask, h->mask_row_words,
-                                                  h->nx, ncell, h->density, scratch);
-    CUDA_TRY(cudaGetLastError());
-    for (int k = 0; k < 4; k++)
-      if (outs[k])
-        CUDA_TRY(cudaMemcpyAsync(outs[k] + done, scratch + (size_t)k * ncell, ncell * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
-    done += ncell;
+    float* scratch = nullptr;
+    int step = 0;
+    int rc = staging(h, s, (size_t)h->nx * 4 * sizeof(float), s.rows, &scratch, &step);
+    if (rc) return rc;
+    for (int r = 0; r < s.rows; r += step) {
+      const size_t ncell = (size_t)std::min(step, s.rows - r) * h->nx;
+      const unsigned blocks = (unsigned)((ncell + 255) / 256);
+      lbm::final_state<<<blocks, 256, 0, s.stream>>>(s.buf[h->inplace ? 0 : h->cur], layout_of(h, s), 1 + r, s.mask,
+                                                    h->mask_row_words, ncell, h->density, scratch);
+      CUDA_TRY(cudaGetLastError());
+      for (int k = 0; k < 4; k++)
+        if (outs[k])
+          CUDA_TRY(cudaMemcpyAsync(outs[k] + done, scratch + (size_t)k * ncell, ncell * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+      done += ncell;
+    }
   }
   return LBM_B200_OK;
 }
@@ -927,6 +1015,8 @@ int lbm_b200_get_final_state(lbm_b200* h, float* u_x, float* u_y, float* u, floa
 int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 {
   if (!h || !key) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  if (h->inplace && (!strcmp(key, "kernel") || !strcmp(key, "min_ctas") || !strcmp(key, "resident")) )
+    return fail(LBM_B200_ERR_STATE, "option '%s' does not apply to an in-place handle", key);
   if (!strcmp(key, "kernel")) {
     if (value < 0 || value > 2) return fail(LBM_B200_ERR_ARG, "kernel must be 0, 1 or 2");
     if (value == 2 && !(h->nx % 4 == 0 && h->nx >= 8)) return fail(LBM_B200_ERR_ARG, "kernel 2 needs nx %% 4 == 0 and nx >= 8");
@@ -943,8 +1033,12 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "resident")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "resident must be -1, 0 or 1");
     h->opt_resident = value;
+  } else if (!strcmp(key, "staging_bytes")) {
+    if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
+    h->opt_staging_bytes = value;
   } else if (!strcmp(key, "cache_hint")) {
     if (value < 0 || value > 4 || value == 3) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1, 2 or 4");
+    if (h->inplace && value > 2) return fail(LBM_B200_ERR_ARG, "cache_hint of an in-place handle must be 0, 1 or 2");
     h->opt_cache_hint = value;
   } else {
     return fail(LBM_B200_ERR_ARG, "unknown option '%s'", key);
@@ -958,7 +1052,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
 {
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
-  if (!strcmp(key, "kernel")) *value = h->resident ? 3 : (use_vec4(h) ? 2 : 1);
+  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1));
+  else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
+  else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;
   else if (!strcmp(key, "ctas_per_sm")) *value = h->opt_ctas_per_sm;
   else if (!strcmp(key, "min_ctas")) *value = h->opt_min_ctas;
@@ -997,6 +1093,7 @@ void lbm_b200_destroy(lbm_b200* h)
     if (s.av_dev) cudaFree(s.av_dev);
     if (s.cursor) cudaFree(s.cursor);
     if (s.blocked_dev) cudaFree(s.blocked_dev);
+    if (s.bounce) cudaFree(s.bounce);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
   }

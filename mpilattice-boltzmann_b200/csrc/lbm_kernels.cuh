@@ -328,6 +328,230 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel 4 ("in place", the AA access pattern): ONE population buffer instead of the ping-pong pair, same
+// 72 B/cell/step.  Every cell reads and writes exactly the same nine memory locations in a step, so a step
+// needs no second buffer and no ordering between cells.  Two alternating step flavours:
+//   NEIGHBOUR (state layout L0 -> L1): pull population i from (slot i, x - c_i) exactly like step_vec4,
+//       collide, and write the post-collision population opp(i) back to that SAME location.  L1 therefore
+//       holds, at (slot i, y), the population that arrives at y travelling in direction opp(i).
+//   LOCAL (L1 -> L0): population j of cell y is at (slot opp(j), y); collide; store population j at
+//       (slot j, y).  All nine accesses are aligned 128-bit row accesses of the cell's own row.
+// L0 is the canonical layout of the ping-pong kernels (post-collision, not yet streamed), so after an even
+// number of steps the buffer is bit-identical to theirs; after an odd number the accessors below decode L1.
+// The arithmetic is the same collide()/accelerate() as everywhere else.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int opposite(int k) { return k == 0 ? 0 : (k <= 4 ? ((k + 1) & 3) + 1 : ((k - 3) & 3) + 5); }
+
+template <int HINT>
+__device__ __forceinline__ float4 ld4_rw(const float* p)
+{
+  if (HINT == 1) return __ldcs(reinterpret_cast<const float4*>(p));
+  if (HINT == 2) return *reinterpret_cast<const float4*>(p);
+  return __ldcg(reinterpret_cast<const float4*>(p));
+}
+template <int HINT>
+__device__ __forceinline__ float ld1_rw(const float* p)
+{
+  if (HINT == 1) return __ldcs(p);
+  if (HINT == 2) return *p;
+  return __ldcg(p);
+}
+template <int HINT>
+__device__ __forceinline__ void st4_rw(float* p, float4 v)
+{
+  if (HINT == 1) __stcs(reinterpret_cast<float4*>(p), v);
+  else *reinterpret_cast<float4*>(p) = v;
+}
+// the first / last three floats of an aligned group of four (the fourth belongs to the neighbouring segment)
+__device__ __forceinline__ void st3_low(float* p, float4 v)
+{
+  *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
+  p[2] = v.z;
+}
+__device__ __forceinline__ void st3_high(float* p, float4 v)
+{
+  p[1] = v.y;
+  *reinterpret_cast<float2*>(p + 2) = make_float2(v.z, v.w);
+}
+
+template <bool NEIGHBOUR, int HINT>
+__device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restrict__ buf, const int accel_row)
+{
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const long nseg = (long)a.row_count * a.chunks;
+  const size_t P = a.plane;
+  double acc = 0.0;
+
+  for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
+    const int ri = (int)(seg / a.chunks);
+    const int ch = (int)(seg - (long)ri * a.chunks);
+    const int row = a.row_begin + ri * a.row_stride;
+    const int x0 = ch * kSegCells + lane * 4;
+    const bool active = x0 < a.nx;
+    const size_t o_c = (size_t)row * a.nx;
+    const unsigned bits = active ? ((__ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5)) >> (x0 & 31)) & 0xFu) : 0u;
+    const bool fold_accel = (row == accel_row);
+    float f[4][9];
+
+    if (!NEIGHBOUR) {
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const float4 v = ld4_rw<HINT>(buf + (size_t)opposite(k) * P + o_c + x0);
+          f[0][k] = v.x; f[1][k] = v.y; f[2][k] = v.z; f[3][k] = v.w;
+        }
+        float u4 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const bool blocked = (bits >> j) & 1u;
+          const float u = collide(f[j], blocked, a.c.omega);
+          u4 = (j == 0) ? u : add(u4, u);
+          if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+        }
+        acc += (double)u4;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+          st4_rw<HINT>(buf + (size_t)k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+      }
+      continue;
+    }
+
+    // ---- NEIGHBOUR flavour: the pull of step_vec4, then the push back into the very same locations ----
+    const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
+    const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
+    const bool west_edge = (lane == 0);
+    const bool east_edge = (lane == 31) || (x0 + 4 >= a.nx);
+    const int xw = (x0 == 0) ? a.nx - 1 : x0 - 1;
+    const int xe = (x0 + 4 >= a.nx) ? 0 : x0 + 4;
+    const size_t o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
+
+    float4 c[9];
+    float w_c = 0.f, w_s = 0.f, w_n = 0.f, e_c = 0.f, e_s = 0.f, e_n = 0.f;
+    if (active) {
+      c[0] = ld4_rw<HINT>(buf + 0 * P + o_c + x0);
+      c[1] = ld4_rw<HINT>(buf + 1 * P + o_c + x0);
+      c[2] = ld4_rw<HINT>(buf + 2 * P + o_s + x0);
+      c[3] = ld4_rw<HINT>(buf + 3 * P + o_c + x0);
+      c[4] = ld4_rw<HINT>(buf + 4 * P + o_n + x0);
+      c[5] = ld4_rw<HINT>(buf + 5 * P + o_s + x0);
+      c[6] = ld4_rw<HINT>(buf + 6 * P + o_s + x0);
+      c[7] = ld4_rw<HINT>(buf + 7 * P + o_n + x0);
+      c[8] = ld4_rw<HINT>(buf + 8 * P + o_n + x0);
+      if (west_edge) {
+        w_c = ld1_rw<HINT>(buf + 1 * P + o_c + xw);
+        w_s = ld1_rw<HINT>(buf + 5 * P + o_s + xw);
+        w_n = ld1_rw<HINT>(buf + 8 * P + o_n + xw);
+      }
+      if (east_edge) {
+        e_c = ld1_rw<HINT>(buf + 3 * P + o_c + xe);
+        e_s = ld1_rw<HINT>(buf + 6 * P + o_s + xe);
+        e_n = ld1_rw<HINT>(buf + 7 * P + o_n + xe);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+    const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+    const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+    const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+    const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+    const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+
+    f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+    f[0][1] = west_edge ? w_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+    f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+    f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = east_edge ? e_c : dn3;
+    f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+    f[0][5] = west_edge ? w_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+    f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = east_edge ? e_s : dn6;
+    f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = east_edge ? e_n : dn7;
+    f[0][8] = west_edge ? w_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+
+    if (active) {
+      float u4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool blocked = (bits >> j) & 1u;
+        const float u = collide(f[j], blocked, a.c.omega);
+        u4 = (j == 0) ? u : add(u4, u);
+        if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+      }
+      acc += (double)u4;
+    }
+    // the value that belongs to the neighbouring lane's aligned group of four: (slot 1, x-1) <- f3(x) etc.
+    const float g3 = __shfl_down_sync(0xffffffffu, f[0][3], 1);
+    const float g7 = __shfl_down_sync(0xffffffffu, f[0][7], 1);
+    const float g6 = __shfl_down_sync(0xffffffffu, f[0][6], 1);
+    const float g1 = __shfl_up_sync(0xffffffffu, f[3][1], 1);
+    const float g8 = __shfl_up_sync(0xffffffffu, f[3][8], 1);
+    const float g5 = __shfl_up_sync(0xffffffffu, f[3][5], 1);
+    if (active) {
+      st4_rw<HINT>(buf + 0 * P + o_c + x0, make_float4(f[0][0], f[1][0], f[2][0], f[3][0]));
+      st4_rw<HINT>(buf + 2 * P + o_s + x0, make_float4(f[0][4], f[1][4], f[2][4], f[3][4]));
+      st4_rw<HINT>(buf + 4 * P + o_n + x0, make_float4(f[0][2], f[1][2], f[2][2], f[3][2]));
+      const float4 v1 = make_float4(f[1][3], f[2][3], f[3][3], g3);   // slot 1, this row
+      const float4 v5 = make_float4(f[1][7], f[2][7], f[3][7], g7);   // slot 5, row below
+      const float4 v8 = make_float4(f[1][6], f[2][6], f[3][6], g6);   // slot 8, row above
+      const float4 v3 = make_float4(g1, f[0][1], f[1][1], f[2][1]);   // slot 3, this row
+      const float4 v6 = make_float4(g8, f[0][8], f[1][8], f[2][8]);   // slot 6, row below
+      const float4 v7 = make_float4(g5, f[0][5], f[1][5], f[2][5]);   // slot 7, row above
+      if (!east_edge) {
+        st4_rw<HINT>(buf + 1 * P + o_c + x0, v1);
+        st4_rw<HINT>(buf + 5 * P + o_s + x0, v5);
+        st4_rw<HINT>(buf + 8 * P + o_n + x0, v8);
+      } else {
+        // the fourth element is the next segment's west scalar; this lane's own east scalars go back too
+        st3_low(buf + 1 * P + o_c + x0, v1);
+        st3_low(buf + 5 * P + o_s + x0, v5);
+        st3_low(buf + 8 * P + o_n + x0, v8);
+        buf[3 * P + o_c + xe] = f[3][1];
+        buf[6 * P + o_s + xe] = f[3][8];
+        buf[7 * P + o_n + xe] = f[3][5];
+      }
+      if (!west_edge) {
+        st4_rw<HINT>(buf + 3 * P + o_c + x0, v3);
+        st4_rw<HINT>(buf + 6 * P + o_s + x0, v6);
+        st4_rw<HINT>(buf + 7 * P + o_n + x0, v7);
+      } else {
+        st3_high(buf + 3 * P + o_c + x0, v3);
+        st3_high(buf + 6 * P + o_s + x0, v6);
+        st3_high(buf + 7 * P + o_n + x0, v7);
+        buf[1 * P + o_c + xw] = f[0][3];
+        buf[5 * P + o_s + xw] = f[0][7];
+        buf[8 * P + o_n + xw] = f[0][6];
+      }
+    }
+  }
+  return acc;
+}
+
+template <bool NEIGHBOUR, int HINT>
+__global__ void __launch_bounds__(256, 2) step_inplace(const StepArgs a)
+{
+  const double acc = inplace_pass<NEIGHBOUR, HINT>(a, a.dst, a.accel_row);
+  block_sum_to(acc, a.partials + blockIdx.x);
+}
+
+// Where the canonical population k of the cell (x, padded row) lives in a single-slab buffer whose layout is
+// L0 (odd = 0: in place) or L1 (odd = 1: at the destination cell, in the opposite slot; periodic in x and y).
+struct Layout {
+  size_t plane;
+  int nx, rows, odd;
+};
+__device__ __forceinline__ size_t locate(const Layout& l, int k, int x, int row)
+{
+  if (!l.odd || k == 0) return (size_t)k * l.plane + (size_t)row * l.nx + x;
+  const int cx = (k == 1 || k == 5 || k == 8) ? 1 : ((k == 3 || k == 6 || k == 7) ? -1 : 0);
+  const int cy = (k == 2 || k == 5 || k == 6) ? 1 : ((k == 4 || k == 7 || k == 8) ? -1 : 0);
+  int xo = x + cx, ro = row + cy;
+  if (xo < 0) xo = l.nx - 1; else if (xo >= l.nx) xo = 0;
+  if (ro < 1) ro = l.rows; else if (ro > l.rows) ro = 1;
+  return (size_t)opposite(k) * l.plane + (size_t)ro * l.nx + xo;
+}
+
+// ---------------------------------------------------------------------------------------
 // Kernel 3 ("resident"): many timesteps in ONE cooperative launch for grids that are launch-latency
 // bound (the shipped 128..1024-wide decks: a step is a few microseconds of work).  The same pass as
 // step_vec4 runs `steps` times with a grid-wide barrier in between and the two buffers swapping roles;
@@ -425,21 +649,23 @@ __global__ void __launch_bounds__(256) step_scalar(const StepArgs a)
 
 // accelerate_flow (d2q9-bgk.c:442-478) as a pre-pass on one row: needed once per run, before
 // the first step; all later steps get their force folded into the previous step's store.
-__global__ void accelerate_row(float* buf, size_t plane, const uint32_t* mask_row, int nx, size_t row_off,
-                               float aw1, float aw2)
+// `l` says where the row's populations live (in place, or decoded from the in-place kernel's L1 layout).
+__global__ void accelerate_row(float* buf, Layout l, const uint32_t* mask_row, int row, float aw1, float aw2)
 {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= nx) return;
+  if (x >= l.nx) return;
   const bool blocked = (mask_row[x >> 5] >> (x & 31)) & 1u;
-  float* p = buf + row_off + x;
-  const float f3 = p[3 * plane], f6 = p[6 * plane], f7 = p[7 * plane];
+  float* p1 = buf + locate(l, 1, x, row); float* p3 = buf + locate(l, 3, x, row);
+  float* p5 = buf + locate(l, 5, x, row); float* p6 = buf + locate(l, 6, x, row);
+  float* p7 = buf + locate(l, 7, x, row); float* p8 = buf + locate(l, 8, x, row);
+  const float f3 = *p3, f6 = *p6, f7 = *p7;
   if (!blocked && sub(f3, aw1) > 0.0f && sub(f6, aw2) > 0.0f && sub(f7, aw2) > 0.0f) {
-    p[1 * plane] = add(p[1 * plane], aw1);
-    p[5 * plane] = add(p[5 * plane], aw2);
-    p[8 * plane] = add(p[8 * plane], aw2);
-    p[3 * plane] = sub(f3, aw1);
-    p[6 * plane] = sub(f6, aw2);
-    p[7 * plane] = sub(f7, aw2);
+    *p1 = add(*p1, aw1);
+    *p5 = add(*p5, aw2);
+    *p8 = add(*p8, aw2);
+    *p3 = sub(f3, aw1);
+    *p6 = sub(f6, aw2);
+    *p7 = sub(f7, aw2);
   }
 }
 
@@ -501,15 +727,17 @@ __global__ void fill_planes(float* buf, size_t plane, float w0, float w1, float 
   for (int k = 5; k < 9; k++) buf[k * plane + i] = w2;
 }
 
-// planes (padded rows [row0, row0+nrows)) -> array of structs, and back
-__global__ void soa_to_aos(const float* buf, size_t plane, size_t first, size_t ncell, float* aos)
+// planes -> array of structs for `ncell` cells starting at padded row `row0`, and back
+__global__ void soa_to_aos(const float* buf, Layout l, int row0, size_t ncell, float* aos)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell * 9) return;
   const size_t cell = i / 9;
   const int k = (int)(i - cell * 9);
-  aos[i] = buf[k * plane + first + cell];
+  const size_t r = cell / l.nx;
+  aos[i] = buf[locate(l, k, (int)(cell - r * l.nx), row0 + (int)r)];
 }
+// always writes the canonical layout (l.odd is ignored)
 __global__ void aos_to_soa(const float* aos, size_t plane, size_t first, size_t ncell, float* buf)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,22 +747,23 @@ __global__ void aos_to_soa(const float* aos, size_t plane, size_t first, size_t 
   buf[k * plane + first + cell] = aos[i];
 }
 
-// Macroscopic fields exactly as write_values computes them (d2q9-bgk.c:1076-1111); out holds
-// four planes of `ncell` floats: u_x, u_y, |u|, pressure.
-__global__ void final_state(const float* buf, size_t plane, size_t first, const uint32_t* mask, int mask_row_words,
-                            int nx, size_t ncell, float density, float* out)
+// Macroscopic fields exactly as write_values computes them (d2q9-bgk.c:1076-1111) for `ncell` cells
+// starting at padded row `row0`; out holds four planes of `ncell` floats: u_x, u_y, |u|, pressure.
+__global__ void final_state(const float* buf, Layout l, int row0, const uint32_t* mask, int mask_row_words,
+                            size_t ncell, float density, float* out)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell) return;
-  const size_t r = i / nx;
-  const int x = (int)(i - r * nx);
-  const bool blocked = (mask[r * mask_row_words + (x >> 5)] >> (x & 31)) & 1u;
+  const size_t r = i / l.nx;
+  const int x = (int)(i - r * l.nx);
+  const int row = row0 + (int)r;
+  const bool blocked = (mask[(size_t)(row - 1) * mask_row_words + (x >> 5)] >> (x & 31)) & 1u;
   constexpr float c_sq = 1.0f / 3.0f;
   float ux = 0.f, uy = 0.f, u = 0.f, pr = mul(density, c_sq);
   if (!blocked) {
     float f[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) f[k] = buf[k * plane + first + i];
+    for (int k = 0; k < 9; k++) f[k] = buf[locate(l, k, x, row)];
     float rho = add(0.0f, f[0]);
 #pragma unroll
     for (int k = 1; k < 9; k++) rho = add(rho, f[k]);

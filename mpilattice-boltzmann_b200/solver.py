@@ -49,11 +49,13 @@ class Simulation:
     """A D2Q9-BGK run on one or more B200s.
 
     Whole-domain form (one process):  Simulation(nx, ny, density, accel, omega, obstacles,
-    n_slabs=1, devices=None, device=None).
+    n_slabs=1, devices=None, device=None).  inplace=True keeps ONE population buffer and streams in
+    place (lbm_b200_create_inplace; one slab, one device).
     Slab form (one rank per process):  Simulation.slab(...), then export_ipc()/connect_ipc().
     """
 
-    def __init__(self, nx, ny, density, accel, omega, obstacles, n_slabs: int = 1, devices=None, device=None):
+    def __init__(self, nx, ny, density, accel, omega, obstacles, n_slabs: int = 1, devices=None, device=None,
+                 inplace: bool = False):
         self._h = handle_t()
         self._lib = library()
         ob = np.ascontiguousarray(obstacles, np.int32)
@@ -66,8 +68,14 @@ class Simulation:
             dev = np.ascontiguousarray(devices, np.int32)
             if dev.shape != (n_slabs,):
                 raise ValueError("devices must list one device per slab")
-        _check(self._lib.lbm_b200_create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
-                                         _ip(dev) if dev is not None else None))
+        if inplace:
+            if n_slabs != 1:
+                raise ValueError("an in-place simulation is a single slab")
+            _check(self._lib.lbm_b200_create_inplace(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob),
+                                                     int(dev[0]) if dev is not None else 0))
+        else:
+            _check(self._lib.lbm_b200_create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
+                                             _ip(dev) if dev is not None else None))
         self.nx, self.ny = nx, ny
         self._set_shape()
 

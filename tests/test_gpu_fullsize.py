@@ -31,6 +31,29 @@ def test_full_size_cylinder_array(pkg, oracle):
     assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
 
 
+def test_full_size_inplace(pkg, oracle):
+    """One 9.66 GB buffer instead of two: 16384 x 16384 in place, an odd and an even number of steps, the state read
+    back through the 256 MB staging buffer (38 chunks), against the tiled 128-wide oracle."""
+    import torch
+    period = 128
+    rng = np.random.default_rng(43)
+    narrow = narrow_pattern(period, rng)
+    cells = oracle.init_cells(period, NY, DENSITY)
+    obstacles = np.tile(narrow, (1, NX // period))
+    free0 = torch.cuda.mem_get_info()[0]
+    with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles, inplace=True) as sim:
+        used = free0 - torch.cuda.mem_get_info()[0]
+        assert used < 1.1 * 36 * NX * NY                     # one buffer (+ mask, partials), not two
+        done = 0
+        for iters in (5, 3):
+            _, av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow), exact=True)
+            av = sim.run(iters)
+            done += iters
+            for got, want in zip(sim.final_state(), oracle.final_state(cells, narrow, DENSITY)):
+                assert np.array_equal(bits(got), bits(np.tile(want, (1, NX // period)))), f"after {done} steps"
+            assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
+
+
 def narrow_pattern(period, rng):
     ob = (rng.random((NY, period)) < 0.02).astype(np.int32)
     ob[0, :] = ob[-1, :] = 1                     # the synthetic deck's channel walls (SURVEY 8d)

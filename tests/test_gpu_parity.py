@@ -232,3 +232,74 @@ def test_cylinder_array_deck(pkg, oracle):
     cells0 = oracle.init_cells(nx, ny, DENSITY)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         assert_parity(sim, oracle, pkg, cells0, obstacles, 60)
+
+
+# ---- in-place streaming (one population buffer, AA access pattern) ---------------------------------
+
+INPLACE_SHAPES = [(128, 24), (256, 7), (136, 19), (200, 33), (8, 8), (12, 5), (1024, 16), (132, 3)]
+
+
+@pytest.mark.parametrize("nx,ny", INPLACE_SHAPES)
+@pytest.mark.parametrize("iters", [1, 2, 17])
+def test_inplace_bit_exact(pkg, oracle, nx, ny, iters):
+    """Odd and even step counts: after an odd one the buffer is in the shifted layout L1, which get_cells and
+    get_final_state decode; ragged side walls exercise the x-wrap, open rows the y-wrap."""
+    rng = np.random.default_rng(nx * 17 + ny + iters)
+    obstacles = random_obstacles(rng, ny, nx, 0.10, walls=(ny % 2 == 0))
+    obstacles[:, 0] = rng.random(ny) < 0.5
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    obstacles[ny - 2, :] = rng.random(nx) < 0.2              # blocked cells inside the accelerated row
+    cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, : nx // 3, 3] = 1e-5                      # cells where the force must not be applied
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, inplace=True) as sim:
+        assert sim.get_option("inplace") == 1 and sim.get_option("kernel") == 4
+        assert np.array_equal(bits(sim.get_cells()), bits(oracle.init_cells(nx, ny, DENSITY)))
+        sim.set_cells(cells0)
+        assert np.array_equal(bits(sim.get_cells()), bits(cells0))
+        ref_cells = assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+        for got, want in zip(sim.final_state(), oracle.final_state(ref_cells, obstacles, DENSITY)):
+            assert np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("hint", [0, 1, 2])
+def test_inplace_runs_compose_across_layout_parities(pkg, oracle, hint):
+    """run(3) + run(4) + run(0) + run(1) + run(5) == run(13): the body-force pre-pass and the un-accelerated last
+    step work from either layout, and set_cells after an odd run returns to the canonical one."""
+    rng = np.random.default_rng(21 + hint)
+    nx, ny = 384, 20
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, 13)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, inplace=True) as sim:
+        sim.set_option("cache_hint", hint)
+        sim.set_option("staging_bytes", 5 * nx * 36)          # five rows per chunk: the staged getters loop
+        sim.run(3)
+        sim.set_cells(cells0)                                # from layout L1 back to a fresh canonical state
+        av = np.concatenate([sim.run(3), sim.run(4), sim.run(0), sim.run(1), sim.run(5)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
+        assert_av(av, ref_av, ref_exact)
+        for got, want in zip(sim.final_state(), oracle.final_state(ref_cells, obstacles, DENSITY)):
+            assert np.array_equal(bits(got), bits(want))
+
+
+def test_inplace_equals_ping_pong_over_a_graph_replayed_run(pkg):
+    """1100 steps of a 256 x 64 grid: CUDA-graph replay of 256-step chunks on both handles; every bit equal,
+    av_vels identical (same partial sums in the same tree when the launch geometry is the same)."""
+    rng = np.random.default_rng(33)
+    nx, ny, iters = 256, 64, 1101
+    obstacles = random_obstacles(rng, ny, nx, 0.04)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as a, \
+            pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, inplace=True) as b:
+        a.set_option("resident", 0)
+        av_a, av_b = a.run(iters), b.run(iters)
+        assert np.array_equal(bits(a.get_cells()), bits(b.get_cells()))
+        assert np.array_equal(bits(av_a), bits(av_b))
+
+
+def test_inplace_rejects_what_it_cannot_do(pkg):
+    ob = np.zeros((9, 30), np.int32)
+    with pytest.raises(pkg.LBMError, match="nx % 4"):
+        pkg.Simulation(30, 9, DENSITY, ACCEL, OMEGA, ob, inplace=True)
+    with pkg.Simulation(32, 9, DENSITY, ACCEL, OMEGA, np.zeros((9, 32), np.int32), inplace=True) as sim:
+        with pytest.raises(pkg.LBMError, match="does not apply"):
+            sim.set_option("kernel", 1)

@@ -30,18 +30,22 @@ def main():
     ap.add_argument("--hints", default="0,1,2")
     ap.add_argument("--graph-steps", default="0")
     ap.add_argument("--resident", default="0")
+    ap.add_argument("--inplace", action="store_true", help="one population buffer (AA access pattern); kernels/min-ctas/resident are ignored")
     args = ap.parse_args()
     pkg = entry.load_package()
     obstacles = pkg.decks.channel_obstacles(args.nx, args.ny)
     results = []
-    with pkg.Simulation(args.nx, args.ny, 0.1, 0.005, 1.85, obstacles) as sim:
+    if args.inplace:
+        args.kernels, args.min_ctas, args.resident = "4", "2", "0"
+    with pkg.Simulation(args.nx, args.ny, 0.1, 0.005, 1.85, obstacles, inplace=args.inplace) as sim:
         lists = [[int(v) for v in s.split(",")] for s in (args.kernels, args.min_ctas, args.ctas_per_sm, args.hints, args.graph_steps, args.resident)]
         for kernel, min_ctas, per_sm, hint, graph, resident in itertools.product(*lists):
             if kernel == 1 and (min_ctas != lists[1][0] or hint != lists[3][0]):
                 continue
-            sim.set_option("resident", resident)
-            sim.set_option("kernel", kernel)
-            sim.set_option("min_ctas", min_ctas)
+            if not args.inplace:
+                sim.set_option("resident", resident)
+                sim.set_option("kernel", kernel)
+                sim.set_option("min_ctas", min_ctas)
             sim.set_option("ctas_per_sm", per_sm)
             sim.set_option("cache_hint", hint)
             sim.set_option("graph_steps", graph)
