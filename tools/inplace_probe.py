@@ -1,0 +1,17 @@
+#!/usr/bin/env python3
+"""Runs a few in-place timesteps at full size (for ncu: per-flavour durations and DRAM bytes)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+pkg = entry.load_package()
+nx = ny = int(os.environ.get("N", 16384))
+steps = int(os.environ.get("STEPS", 6))
+with pkg.Simulation(nx, ny, 0.1, 0.005, 1.85, pkg.decks.channel_obstacles(nx, ny), inplace=bool(int(os.environ.get("INPLACE", 1)))) as sim:
+    sim.set_option("graph_steps", 0)
+    sim.enqueue(steps)
+    sim.sync()
+    print("ms per step", sim.elapsed_ms() / steps)
