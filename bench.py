@@ -191,8 +191,9 @@ def workload_config(args, n):
         "nx": args.nx, "ny_per_gpu": ny_global // n, "ny_global": ny_global,
         "timesteps_per_step": args.timesteps,
         "density": DENSITY, "accel": ACCEL, "omega": OMEGA,
-        "layout": "fp32 SoA, 9 planes, ping-pong; 1-bit obstacle mask",
-        "l2": f"no L2 flush needed: {2 * 9 * 4 * args.nx * (ny_global // n) / 1e9:.1f} GB of state per GPU streams through the 126 MB L2 every timestep",
+        "layout": ("fp32 SoA, 9 planes, ONE buffer streamed in place (AA access pattern); 1-bit obstacle mask"
+                   if getattr(args, "inplace", False) else "fp32 SoA, 9 planes, ping-pong; 1-bit obstacle mask"),
+        "l2": f"no L2 flush needed: {(1 if getattr(args, 'inplace', False) else 2) * 9 * 4 * args.nx * (ny_global // n) / 1e9:.1f} GB of state per GPU streams through the 126 MB L2 every timestep",
         "parallelism": f"row-slab x{n}" + (", halo rows as NVLink stores from the edge-row kernel" if n > 1 else ""),
     }
 
@@ -266,16 +267,17 @@ def bench_ours(args, pkg):
 
     def make_sim():
         if n == 1:
-            sim = pkg.Simulation(nx, rows, DENSITY, ACCEL, OMEGA, obstacles, device=local)
+            sim = pkg.Simulation(nx, rows, DENSITY, ACCEL, OMEGA, obstacles, device=local, inplace=args.inplace)
         else:
-            sim = pkg.Simulation.slab(nx, ny_global, first, rows, rank, n, DENSITY, ACCEL, OMEGA, inv, obstacles, device=local)
+            sim = pkg.Simulation.slab(nx, ny_global, first, rows, rank, n, DENSITY, ACCEL, OMEGA, inv, obstacles, device=local,
+                                      inplace=args.inplace)
             blobs = [None] * n
             dist.all_gather_object(blobs, sim.export_ipc())
             sim.connect_ipc(blobs[(rank - 1) % n], blobs[(rank + 1) % n])
             dist.barrier()
         for key in ("kernel", "graph_steps", "ctas_per_sm", "min_ctas"):
             v = getattr(args, key)
-            if v is not None:
+            if v is not None and not (args.inplace and key in ("kernel", "min_ctas")):
                 sim.set_option(key, v)
         return sim
 
@@ -326,6 +328,8 @@ def bench_ours(args, pkg):
     t1 = time.perf_counter()
     sim.enqueue(timesteps)
     sim.fetch_av_vels(timesteps, av_t.numpy())        # D2H: per-step averages (synchronises)
+    if args.inplace and distributed:
+        dist.barrier()                                # in place, edge-row populations may live in the neighbours' buffers
     t2 = time.perf_counter()
     sim.final_state(fields_t.numpy())                 # D2H: u_x, u_y, |u|, pressure
     t3 = time.perf_counter()
@@ -347,7 +351,7 @@ def bench_ours(args, pkg):
             "metric": "MLUPS", "value": round(value, 1), "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W,
             "ms_per_step": round(device_ms / K, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "kernel": {1: "step_scalar", 2: "step_vec4"}.get(kernel, str(kernel)),
+            "kernel": {1: "step_scalar", 2: "step_vec4", 3: "steps_resident", 4: "step_inplace"}.get(kernel, str(kernel)),
             "wall_ms_per_step": round(wall_s * 1e3 / K, 4),
             "av_vels_last": float(av[-1]),
             "e2e": {"value": round(e2e_value, 1), "unit": "MLUPS", "h2d_bytes_per_step": h2d // K,
@@ -386,6 +390,8 @@ def main():
     ap.add_argument("--ctas-per-sm", dest="ctas_per_sm", type=int, default=None)
     ap.add_argument("--min-ctas", dest="min_ctas", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inplace", action="store_true",
+                    help="one population buffer per GPU, streamed in place (half the memory, same traffic)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak: --ny rows per GPU (default); strong: --ny rows in total, split over the GPUs")
     args = ap.parse_args()

@@ -73,14 +73,13 @@ int lbm_b200_device_count(void);
 int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                     const int* obstacles, int n_slabs, const int* devices);
 
-/* As lbm_b200_create with one slab on `device`, but with ONE population buffer instead of the reference's
- * cells/tmp_cells pair (d2q9-bgk.c:865-872, swapped at 376-378): the timestep streams in place (the "AA"
- * access pattern: steps alternate between a neighbour-access and a cell-local flavour, csrc/lbm_kernels.cuh
- * kernel 4).  Half the device memory per cell (36 B + 1 bit), the same 72 B/cell/step of traffic and
- * bit-identical results; state in/out is staged through a bounded 256 MB buffer.  Requires nx % 4 == 0,
- * nx >= 8.  Single device only. */
+/* As lbm_b200_create, but with ONE population buffer per slab instead of the reference's cells/tmp_cells pair
+ * (d2q9-bgk.c:865-872, swapped at 376-378): the timestep streams in place (the "AA" access pattern: steps
+ * alternate between a neighbour-access and a cell-local flavour, csrc/lbm_kernels.cuh kernel 4).  Half the
+ * device memory per cell (36 B + 1 bit), the same 72 B/cell/step of traffic and bit-identical results; state
+ * in/out is staged through a bounded buffer ("staging_bytes").  Requires nx % 4 == 0, nx >= 8. */
 int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
-                            const int* obstacles, int device);
+                            const int* obstacles, int n_slabs, const int* devices);
 
 /* ---- one slab per process (one rank per GPU; ranks launched by torchrun or similar) --- */
 
@@ -91,6 +90,13 @@ int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, fl
 int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
                          int rank, int n_ranks, float density, float accel, float omega,
                          float free_cells_inv, const int* obstacles_slab, int device);
+
+/* The in-place twin of lbm_b200_create_slab (see lbm_b200_create_inplace); every rank of a ring must use the
+ * same kind.  After an odd number of timesteps the populations of a slab's edge rows live in the neighbours'
+ * buffers: call the state getters only when every rank has finished its run (lbm_b200_sync + a barrier). */
+int lbm_b200_create_slab_inplace(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                                 int rank, int n_ranks, float density, float accel, float omega,
+                                 float free_cells_inv, const int* obstacles_slab, int device);
 
 /* Size in bytes of the blob written by lbm_b200_ipc_export. */
 int lbm_b200_ipc_blob_bytes(void);

@@ -26,7 +26,11 @@ SIGNATURES = {
     "lbm_b200_create": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, c_int_p, ctypes.c_int, c_int_p]),
     "lbm_b200_create_inplace": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_float,
-                                               ctypes.c_float, ctypes.c_float, c_int_p, ctypes.c_int]),
+                                               ctypes.c_float, ctypes.c_float, c_int_p, ctypes.c_int, c_int_p]),
+    "lbm_b200_create_slab_inplace": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                    c_int_p, ctypes.c_int]),
     "lbm_b200_create_slab": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                             ctypes.c_float, ctypes.c_float, c_int_p, ctypes.c_int]),

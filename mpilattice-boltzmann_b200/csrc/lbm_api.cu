@@ -87,6 +87,7 @@ struct IpcBlob {
   int rows;
   int device;
   int pid;
+  int inplace;
 };
 
 constexpr int kMaxCtasPerSm = 128;      // upper bound of the oversubscribed grid, in CTAs per SM
@@ -155,7 +156,7 @@ void plan_region(const lbm_b200* h, int device, int rows, int* threads, int* gri
       const int fit = occupancy(lbm::steps_resident<2>, *threads);
       per_sm = per_sm > 0 ? std::min(per_sm, fit) : fit;
     } else if (per_sm <= 0) {
-      per_sm = h->inplace               ? occupancy(lbm::step_inplace<true, 0>, *threads)
+      per_sm = h->inplace               ? occupancy(lbm::step_inplace<true, false, 0>, *threads)
                : (h->opt_min_ctas >= 4) ? occupancy(lbm::step_vec4<false, 4, 0>, *threads)
                : (h->opt_min_ctas == 3) ? occupancy(lbm::step_vec4<false, 3, 0>, *threads)
                                         : occupancy(lbm::step_vec4<false, 2, 0>, *threads);
@@ -308,7 +309,12 @@ int ensure_partials(lbm_b200* h)
 // where the canonical populations of the current state live (see lbm::locate)
 lbm::Layout layout_of(const lbm_b200* h, const Slab& s)
 {
-  return lbm::Layout{s.plane, h->nx, s.rows, h->inplace ? h->cur : 0};
+  lbm::Layout l{};
+  l.plane = s.plane; l.nx = h->nx; l.rows = s.rows; l.odd = h->inplace ? h->cur : 0;
+  const bool ring = h->n_ranks > 1;
+  l.south = ring ? s.south.buf[0] : s.buf[0]; l.south_plane = ring ? s.south.plane : s.plane; l.south_rows = ring ? s.south.rows : s.rows;
+  l.north = ring ? s.north.buf[0] : s.buf[0]; l.north_plane = ring ? s.north.plane : s.plane;
+  return l;
 }
 
 // Device staging for state in/out: the idle ping-pong buffer, or (in-place handles, which have none) a
@@ -358,6 +364,13 @@ void peer_args(const lbm_b200* h, const Slab& s, StepArgs& a)
   a.north_of_last = s.rows + 1;
   a.north_dst = s.north.buf[h->cur ^ 1]; a.north_plane = s.north.plane; a.north_row = 0;
   a.south_dst = s.south.buf[h->cur ^ 1]; a.south_plane = s.south.plane; a.south_row = s.south.rows + 1;
+  if (h->inplace) {
+    // one buffer per slab; the NEIGHBOUR flavour (layout L0 -> L1) writes into the neighbours' owned edge rows,
+    // the LOCAL flavour pushes copies into their halo rows like the ping-pong kernel
+    a.north_dst = s.north.buf[0];
+    a.south_dst = s.south.buf[0];
+    if (h->cur == 0) { a.north_row = 1; a.south_row = s.south.rows; }
+  }
   a.wait_from_south = s.flags + kFromSouth;
   a.wait_from_north = s.flags + kFromNorth;
   a.signal_north = s.north.flags + kFromSouth;     // I am my northern neighbour's south
@@ -397,23 +410,30 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
 {
   if (h->inplace) {
     // one buffer: the NEIGHBOUR flavour takes layout L0 to L1, the LOCAL flavour takes it back
-    Slab& s = h->slabs[0];
-    CUDA_TRY(cudaSetDevice(s.device));
-    StepArgs a = base_args(h, s, slot, fold_accel);
-    a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
-    a.south_of_first = s.rows;
-    a.north_of_last = 1;
-    h->launches++;
-#define LBM_LAUNCH_INPLACE(H)                                                                      \
-  do {                                                                                             \
-    if (h->cur == 0) lbm::step_inplace<true, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);  \
-    else lbm::step_inplace<false, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);             \
+    for (Slab& s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      StepArgs a = base_args(h, s, slot, fold_accel);
+      a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+      h->launches++;
+      if (h->n_ranks == 1) {
+        a.south_of_first = s.rows;
+        a.north_of_last = 1;
+#define LBM_LAUNCH_INPLACE(H)                                                                             \
+  do {                                                                                                    \
+    if (h->cur == 0) lbm::step_inplace<true, false, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);  \
+    else lbm::step_inplace<false, false, H><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);             \
   } while (0)
-    if (h->opt_cache_hint == 1) LBM_LAUNCH_INPLACE(1);
-    else if (h->opt_cache_hint == 2) LBM_LAUNCH_INPLACE(2);
-    else LBM_LAUNCH_INPLACE(0);
+        if (h->opt_cache_hint == 1) LBM_LAUNCH_INPLACE(1);
+        else if (h->opt_cache_hint == 2) LBM_LAUNCH_INPLACE(2);
+        else LBM_LAUNCH_INPLACE(0);
 #undef LBM_LAUNCH_INPLACE
-    CUDA_TRY(cudaGetLastError());
+      } else {
+        peer_args(h, s, a);
+        if (h->cur == 0) lbm::step_inplace<true, true, 0><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);
+        else lbm::step_inplace<false, true, 0><<<s.grid_full, s.threads_full, 0, s.stream>>>(a);
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
   } else if (h->n_ranks == 1) {
     Slab& s = h->slabs[0];
     CUDA_TRY(cudaSetDevice(s.device));
@@ -684,17 +704,19 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
 }
 
 int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
-                            const int* obstacles, int device)
+                            const int* obstacles, int n_slabs, const int* devices)
 {
-  return create_whole(handle, nx, ny, density, accel, omega, obstacles, 1, &device, true);
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, n_slabs, devices, true);
 }
 
-int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
-                         int rank, int n_ranks, float density, float accel, float omega,
-                         float free_cells_inv, const int* obstacles_slab, int device)
+static int create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                       int rank, int n_ranks, float density, float accel, float omega,
+                       float free_cells_inv, const int* obstacles_slab, int device, bool inplace)
 {
   int rc = check_common(nx, ny_global, omega, obstacles_slab, handle);
   if (rc) return rc;
+  if (inplace && !(nx % 4 == 0 && nx >= 8))
+    return fail(LBM_B200_ERR_ARG, "in-place streaming needs nx %% 4 == 0 and nx >= 8 (got %d)", nx);
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LBM_B200_ERR_ARG, "bad rank %d of %d", rank, n_ranks);
   if (rows < 3 || first_row < 0 || first_row + rows > ny_global) return fail(LBM_B200_ERR_ARG, "bad slab rows [%d, %d) of %d (at least 3 rows)", first_row, first_row + rows, ny_global);
   if (n_ranks == 1 && rows != ny_global) return fail(LBM_B200_ERR_ARG, "a single rank must own the whole grid");
@@ -704,6 +726,8 @@ int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row
 
   lbm_b200* h = new lbm_b200();
   init_common(h, nx, ny_global, density, accel, omega, free_cells_inv);
+  h->inplace = inplace;
+  if (inplace) { h->opt_kernel = 0; if (h->opt_cache_hint > 2) h->opt_cache_hint = 0; }
   h->n_ranks = n_ranks;
   h->rank0 = rank;
   h->multi_process = n_ranks > 1;
@@ -723,6 +747,22 @@ int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row
   return LBM_B200_OK;
 }
 
+int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                         int rank, int n_ranks, float density, float accel, float omega,
+                         float free_cells_inv, const int* obstacles_slab, int device)
+{
+  return create_slab(handle, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
+                     obstacles_slab, device, false);
+}
+
+int lbm_b200_create_slab_inplace(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                                 int rank, int n_ranks, float density, float accel, float omega,
+                                 float free_cells_inv, const int* obstacles_slab, int device)
+{
+  return create_slab(handle, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
+                     obstacles_slab, device, true);
+}
+
 int lbm_b200_ipc_blob_bytes(void) { return (int)sizeof(IpcBlob); }
 
 int lbm_b200_ipc_export(lbm_b200* h, void* blob)
@@ -733,16 +773,16 @@ int lbm_b200_ipc_export(lbm_b200* h, void* blob)
   IpcBlob b{};
   CUDA_TRY(cudaSetDevice(s.device));
   CUDA_TRY(cudaIpcGetMemHandle(&b.buf[0], s.buf[0]));
-  CUDA_TRY(cudaIpcGetMemHandle(&b.buf[1], s.buf[1]));
+  if (!h->inplace) CUDA_TRY(cudaIpcGetMemHandle(&b.buf[1], s.buf[1]));
   CUDA_TRY(cudaIpcGetMemHandle(&b.flags, s.flags));
-  b.plane = s.plane; b.rows = s.rows; b.device = s.device; b.pid = (int)getpid();
+  b.plane = s.plane; b.rows = s.rows; b.device = s.device; b.pid = (int)getpid(); b.inplace = h->inplace ? 1 : 0;
   memcpy(blob, &b, sizeof b);
   return LBM_B200_OK;
 }
 
 static int open_neighbour(Neighbour& n, const IpcBlob& b)
 {
-  for (int i = 0; i < 2; i++) CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+  for (int i = 0; i < (b.inplace ? 1 : 2); i++) CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
   CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
   n.plane = (size_t)b.plane; n.rows = b.rows; n.ipc = true;
   return LBM_B200_OK;
@@ -757,6 +797,8 @@ int lbm_b200_ipc_connect(lbm_b200* h, const void* south_blob, const void* north_
   IpcBlob sb, nb;
   memcpy(&sb, south_blob, sizeof sb);
   memcpy(&nb, north_blob, sizeof nb);
+  if ((sb.inplace != 0) != h->inplace || (nb.inplace != 0) != h->inplace)
+    return fail(LBM_B200_ERR_ARG, "ring neighbours must all be in-place handles or all ping-pong handles");
   CUDA_TRY(cudaSetDevice(s.device));
   int rc = open_neighbour(s.south, sb);
   if (rc) return rc;

@@ -374,7 +374,14 @@ __device__ __forceinline__ void st3_high(float* p, float4 v)
   *reinterpret_cast<float2*>(p + 2) = make_float2(v.z, v.w);
 }
 
-template <bool NEIGHBOUR, int HINT>
+// PEER = true: a slab of a multi-GPU ring.  As in step_vec4<PEER> the two edge rows are the first work items of
+// the launch and carry the flag handshake.  What crosses the slab boundary:
+//   LOCAL flavour      (-> L0) copies of planes 2,5,6 of the last row go to the northern neighbour's halo row 0 and
+//                      planes 4,7,8 of the first row to the southern neighbour's halo row rows+1 (as step_vec4);
+//   NEIGHBOUR flavour  (-> L1) pulls from the local halo rows, and the values it would write back into a halo row are
+//                      stored straight into the neighbour's OWNED edge row instead (its row `rows` / row 1), which is
+//                      where the neighbour's next LOCAL step reads them -- nobody else touches those slots.
+template <bool NEIGHBOUR, bool PEER, int HINT>
 __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restrict__ buf, const int accel_row)
 {
   const int lane = threadIdx.x & 31;
@@ -384,9 +391,27 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
   double acc = 0.0;
 
   for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
-    const int ri = (int)(seg / a.chunks);
-    const int ch = (int)(seg - (long)ri * a.chunks);
-    const int row = a.row_begin + ri * a.row_stride;
+    int row, ch;
+    bool edge = false;
+    if (PEER) {
+      const long e2 = 2L * a.chunks;
+      if (seg < e2) {
+        edge = true;
+        const bool first = seg < a.chunks;
+        row = first ? a.row_first : a.row_last;
+        ch = (int)(first ? seg : seg - a.chunks);
+        warp_peer_wait(a);
+      } else {
+        const long s2 = seg - e2;
+        const int ri = (int)(s2 / a.chunks);
+        ch = (int)(s2 - (long)ri * a.chunks);
+        row = a.row_first + 1 + ri;
+      }
+    } else {
+      const int ri = (int)(seg / a.chunks);
+      ch = (int)(seg - (long)ri * a.chunks);
+      row = a.row_begin + ri * a.row_stride;
+    }
     const int x0 = ch * kSegCells + lane * 4;
     const bool active = x0 < a.nx;
     const size_t o_c = (size_t)row * a.nx;
@@ -413,7 +438,22 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
 #pragma unroll
         for (int k = 0; k < 9; k++)
           st4_rw<HINT>(buf + (size_t)k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+        if (PEER) {
+          if (row == a.row_last) {
+            const size_t o = (size_t)a.north_row * a.nx + x0;
+            *reinterpret_cast<float4*>(a.north_dst + 2 * a.north_plane + o) = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
+            *reinterpret_cast<float4*>(a.north_dst + 5 * a.north_plane + o) = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
+            *reinterpret_cast<float4*>(a.north_dst + 6 * a.north_plane + o) = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
+          }
+          if (row == a.row_first) {
+            const size_t o = (size_t)a.south_row * a.nx + x0;
+            *reinterpret_cast<float4*>(a.south_dst + 4 * a.south_plane + o) = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
+            *reinterpret_cast<float4*>(a.south_dst + 7 * a.south_plane + o) = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
+            *reinterpret_cast<float4*>(a.south_dst + 8 * a.south_plane + o) = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
+          }
+        }
       }
+      if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
       continue;
     }
 
@@ -488,9 +528,17 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
     const float g8 = __shfl_up_sync(0xffffffffu, f[3][8], 1);
     const float g5 = __shfl_up_sync(0xffffffffu, f[3][5], 1);
     if (active) {
+      // where the rows below / above are written: the rows just read, or (slab edge rows of a ring) the
+      // neighbour's owned edge row over NVLink
+      float* bs = buf; float* bn = buf;
+      size_t Ps = P, Pn = P, w_s_off = o_s, w_n_off = o_n;
+      if (PEER) {
+        if (row == a.row_first) { bs = a.south_dst; Ps = a.south_plane; w_s_off = (size_t)a.south_row * a.nx; }
+        if (row == a.row_last) { bn = a.north_dst; Pn = a.north_plane; w_n_off = (size_t)a.north_row * a.nx; }
+      }
       st4_rw<HINT>(buf + 0 * P + o_c + x0, make_float4(f[0][0], f[1][0], f[2][0], f[3][0]));
-      st4_rw<HINT>(buf + 2 * P + o_s + x0, make_float4(f[0][4], f[1][4], f[2][4], f[3][4]));
-      st4_rw<HINT>(buf + 4 * P + o_n + x0, make_float4(f[0][2], f[1][2], f[2][2], f[3][2]));
+      st4_rw<HINT>(bs + 2 * Ps + w_s_off + x0, make_float4(f[0][4], f[1][4], f[2][4], f[3][4]));
+      st4_rw<HINT>(bn + 4 * Pn + w_n_off + x0, make_float4(f[0][2], f[1][2], f[2][2], f[3][2]));
       const float4 v1 = make_float4(f[1][3], f[2][3], f[3][3], g3);   // slot 1, this row
       const float4 v5 = make_float4(f[1][7], f[2][7], f[3][7], g7);   // slot 5, row below
       const float4 v8 = make_float4(f[1][6], f[2][6], f[3][6], g6);   // slot 8, row above
@@ -499,56 +547,68 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
       const float4 v7 = make_float4(g5, f[0][5], f[1][5], f[2][5]);   // slot 7, row above
       if (!east_edge) {
         st4_rw<HINT>(buf + 1 * P + o_c + x0, v1);
-        st4_rw<HINT>(buf + 5 * P + o_s + x0, v5);
-        st4_rw<HINT>(buf + 8 * P + o_n + x0, v8);
+        st4_rw<HINT>(bs + 5 * Ps + w_s_off + x0, v5);
+        st4_rw<HINT>(bn + 8 * Pn + w_n_off + x0, v8);
       } else {
         // the fourth element is the next segment's west scalar; this lane's own east scalars go back too
         st3_low(buf + 1 * P + o_c + x0, v1);
-        st3_low(buf + 5 * P + o_s + x0, v5);
-        st3_low(buf + 8 * P + o_n + x0, v8);
+        st3_low(bs + 5 * Ps + w_s_off + x0, v5);
+        st3_low(bn + 8 * Pn + w_n_off + x0, v8);
         buf[3 * P + o_c + xe] = f[3][1];
-        buf[6 * P + o_s + xe] = f[3][8];
-        buf[7 * P + o_n + xe] = f[3][5];
+        bs[6 * Ps + w_s_off + xe] = f[3][8];
+        bn[7 * Pn + w_n_off + xe] = f[3][5];
       }
       if (!west_edge) {
         st4_rw<HINT>(buf + 3 * P + o_c + x0, v3);
-        st4_rw<HINT>(buf + 6 * P + o_s + x0, v6);
-        st4_rw<HINT>(buf + 7 * P + o_n + x0, v7);
+        st4_rw<HINT>(bs + 6 * Ps + w_s_off + x0, v6);
+        st4_rw<HINT>(bn + 7 * Pn + w_n_off + x0, v7);
       } else {
         st3_high(buf + 3 * P + o_c + x0, v3);
-        st3_high(buf + 6 * P + o_s + x0, v6);
-        st3_high(buf + 7 * P + o_n + x0, v7);
+        st3_high(bs + 6 * Ps + w_s_off + x0, v6);
+        st3_high(bn + 7 * Pn + w_n_off + x0, v7);
         buf[1 * P + o_c + xw] = f[0][3];
-        buf[5 * P + o_s + xw] = f[0][7];
-        buf[8 * P + o_n + xw] = f[0][6];
+        bs[5 * Ps + w_s_off + xw] = f[0][7];
+        bn[8 * Pn + w_n_off + xw] = f[0][6];
       }
     }
+    if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
   }
   return acc;
 }
 
-template <bool NEIGHBOUR, int HINT>
+// Loads of a ring slab are always L2-coherent (HINT 0): halo rows and edge-row slots are written by another GPU.
+template <bool NEIGHBOUR, bool PEER, int HINT>
 __global__ void __launch_bounds__(256, 2) step_inplace(const StepArgs a)
 {
-  const double acc = inplace_pass<NEIGHBOUR, HINT>(a, a.dst, a.accel_row);
+  const double acc = inplace_pass<NEIGHBOUR, PEER, PEER ? 0 : HINT>(a, a.dst, a.accel_row);
   block_sum_to(acc, a.partials + blockIdx.x);
 }
 
-// Where the canonical population k of the cell (x, padded row) lives in a single-slab buffer whose layout is
-// L0 (odd = 0: in place) or L1 (odd = 1: at the destination cell, in the opposite slot; periodic in x and y).
+// Where the canonical population k of the cell (x, padded row) lives: in place (odd = 0: layout L0), or
+// (odd = 1: layout L1 of the in-place kernels) at the destination cell in the opposite slot -- periodic in x,
+// and across the slab's first / last row in the ring neighbour's owned edge row (the slab itself when it is the
+// whole grid).
 struct Layout {
   size_t plane;
   int nx, rows, odd;
+  const float* south; size_t south_plane; int south_rows;   // owner of the row below row 1, and its last owned row
+  const float* north; size_t north_plane;                   // owner of the row above row `rows` (its row 1)
 };
-__device__ __forceinline__ size_t locate(const Layout& l, int k, int x, int row)
+__device__ __forceinline__ const float* locate(const Layout& l, const float* buf, int k, int x, int row)
 {
-  if (!l.odd || k == 0) return (size_t)k * l.plane + (size_t)row * l.nx + x;
+  if (!l.odd || k == 0) return buf + (size_t)k * l.plane + (size_t)row * l.nx + x;
   const int cx = (k == 1 || k == 5 || k == 8) ? 1 : ((k == 3 || k == 6 || k == 7) ? -1 : 0);
   const int cy = (k == 2 || k == 5 || k == 6) ? 1 : ((k == 4 || k == 7 || k == 8) ? -1 : 0);
-  int xo = x + cx, ro = row + cy;
+  int xo = x + cx;
+  const int ro = row + cy;
   if (xo < 0) xo = l.nx - 1; else if (xo >= l.nx) xo = 0;
-  if (ro < 1) ro = l.rows; else if (ro > l.rows) ro = 1;
-  return (size_t)opposite(k) * l.plane + (size_t)ro * l.nx + xo;
+  if (ro < 1) return l.south + (size_t)opposite(k) * l.south_plane + (size_t)l.south_rows * l.nx + xo;
+  if (ro > l.rows) return l.north + (size_t)opposite(k) * l.north_plane + (size_t)l.nx + xo;
+  return buf + (size_t)opposite(k) * l.plane + (size_t)ro * l.nx + xo;
+}
+__device__ __forceinline__ float* locate(const Layout& l, float* buf, int k, int x, int row)
+{
+  return const_cast<float*>(locate(l, const_cast<const float*>(buf), k, x, row));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -655,9 +715,9 @@ __global__ void accelerate_row(float* buf, Layout l, const uint32_t* mask_row, i
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= l.nx) return;
   const bool blocked = (mask_row[x >> 5] >> (x & 31)) & 1u;
-  float* p1 = buf + locate(l, 1, x, row); float* p3 = buf + locate(l, 3, x, row);
-  float* p5 = buf + locate(l, 5, x, row); float* p6 = buf + locate(l, 6, x, row);
-  float* p7 = buf + locate(l, 7, x, row); float* p8 = buf + locate(l, 8, x, row);
+  float* p1 = locate(l, buf, 1, x, row); float* p3 = locate(l, buf, 3, x, row);
+  float* p5 = locate(l, buf, 5, x, row); float* p6 = locate(l, buf, 6, x, row);
+  float* p7 = locate(l, buf, 7, x, row); float* p8 = locate(l, buf, 8, x, row);
   const float f3 = *p3, f6 = *p6, f7 = *p7;
   if (!blocked && sub(f3, aw1) > 0.0f && sub(f6, aw2) > 0.0f && sub(f7, aw2) > 0.0f) {
     *p1 = add(*p1, aw1);
@@ -735,7 +795,7 @@ __global__ void soa_to_aos(const float* buf, Layout l, int row0, size_t ncell, f
   const size_t cell = i / 9;
   const int k = (int)(i - cell * 9);
   const size_t r = cell / l.nx;
-  aos[i] = buf[locate(l, k, (int)(cell - r * l.nx), row0 + (int)r)];
+  aos[i] = *locate(l, buf, k, (int)(cell - r * l.nx), row0 + (int)r);
 }
 // always writes the canonical layout (l.odd is ignored)
 __global__ void aos_to_soa(const float* aos, size_t plane, size_t first, size_t ncell, float* buf)
@@ -763,7 +823,7 @@ __global__ void final_state(const float* buf, Layout l, int row0, const uint32_t
   if (!blocked) {
     float f[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) f[k] = buf[locate(l, k, x, row)];
+    for (int k = 0; k < 9; k++) f[k] = *locate(l, buf, k, x, row);
     float rho = add(0.0f, f[0]);
 #pragma unroll
     for (int k = 1; k < 9; k++) rho = add(rho, f[k]);

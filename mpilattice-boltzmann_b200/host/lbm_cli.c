@@ -17,6 +17,8 @@
  *   LBM_DEVICES       comma list of CUDA device ids, one per slab (default 0,1,2,...)
  *   LBM_FINAL_STATE   0 = do not write final_state.dat (for decks whose text would be GBs;
  *                     the reference does the same under -DPROFILE, d2q9-bgk.c:419-421)
+ *   LBM_INPLACE       1 = one population buffer per slab, streamed in place (lbm_b200_create_inplace):
+ *                     half the device memory, same results; needs nx % 4 == 0
  *   LBM_VERBOSE       1 = also print MLUPS and effective GB/s on stderr
  */
 #include <math.h>
@@ -191,7 +193,11 @@ int main(int argc, char* argv[])
   /* device allocation + upload sit with initialise(), outside the timed region, exactly
    * where the reference mallocs and scatters (d2q9-bgk.c:208-209 precede tic at 278) */
   lbm_b200* sim = NULL;
-  LBM_TRY(lbm_b200_create(&sim, p.nx, p.ny, p.density, p.accel, p.omega, obstacles, n_slabs, devices));
+  env = getenv("LBM_INPLACE");
+  if (env && atoi(env) == 1)
+    LBM_TRY(lbm_b200_create_inplace(&sim, p.nx, p.ny, p.density, p.accel, p.omega, obstacles, n_slabs, devices));
+  else
+    LBM_TRY(lbm_b200_create(&sim, p.nx, p.ny, p.density, p.accel, p.omega, obstacles, n_slabs, devices));
   float* av_vels = (float*)malloc(sizeof(float) * (size_t)(p.max_iters > 0 ? p.max_iters : 1));
   if (av_vels == NULL) die("cannot allocate memory for av_vels", __LINE__, __FILE__);
 

@@ -49,8 +49,8 @@ class Simulation:
     """A D2Q9-BGK run on one or more B200s.
 
     Whole-domain form (one process):  Simulation(nx, ny, density, accel, omega, obstacles,
-    n_slabs=1, devices=None, device=None).  inplace=True keeps ONE population buffer and streams in
-    place (lbm_b200_create_inplace; one slab, one device).
+    n_slabs=1, devices=None, device=None).  inplace=True keeps ONE population buffer per slab and streams in
+    place (lbm_b200_create_inplace).
     Slab form (one rank per process):  Simulation.slab(...), then export_ipc()/connect_ipc().
     """
 
@@ -68,28 +68,24 @@ class Simulation:
             dev = np.ascontiguousarray(devices, np.int32)
             if dev.shape != (n_slabs,):
                 raise ValueError("devices must list one device per slab")
-        if inplace:
-            if n_slabs != 1:
-                raise ValueError("an in-place simulation is a single slab")
-            _check(self._lib.lbm_b200_create_inplace(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob),
-                                                     int(dev[0]) if dev is not None else 0))
-        else:
-            _check(self._lib.lbm_b200_create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
-                                             _ip(dev) if dev is not None else None))
+        create = self._lib.lbm_b200_create_inplace if inplace else self._lib.lbm_b200_create
+        _check(create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
+                      _ip(dev) if dev is not None else None))
         self.nx, self.ny = nx, ny
         self._set_shape()
 
     @classmethod
     def slab(cls, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
-             obstacles_slab, device):
+             obstacles_slab, device, inplace: bool = False):
         self = cls.__new__(cls)
         self._h = handle_t()
         self._lib = library()
         ob = np.ascontiguousarray(obstacles_slab, np.int32)
         if ob.shape != (rows, nx):
             raise ValueError(f"obstacles_slab must have shape ({rows}, {nx}), got {ob.shape}")
-        _check(self._lib.lbm_b200_create_slab(ctypes.byref(self._h), nx, ny_global, first_row, rows, rank, n_ranks,
-                                              density, accel, omega, free_cells_inv, _ip(ob), device))
+        create = self._lib.lbm_b200_create_slab_inplace if inplace else self._lib.lbm_b200_create_slab
+        _check(create(ctypes.byref(self._h), nx, ny_global, first_row, rows, rank, n_ranks,
+                      density, accel, omega, free_cells_inv, _ip(ob), device))
         self.nx, self.ny = nx, ny_global
         self._set_shape()
         return self

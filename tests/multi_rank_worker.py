@@ -20,12 +20,13 @@ def main(out_path):
     local = int(os.environ.get("LOCAL_RANK", rank))
     pkg = entry.load_package()
     dist.init_process_group("gloo")
-    nx, ny, iters = 384, 16 * size + 3, 300
+    inplace = os.environ.get("LBM_TEST_INPLACE") == "1"
+    nx, ny, iters = 384, 16 * size + 3, 301 if inplace else 300   # in place: end in the shifted layout L1
     obstacles = random_obstacles(np.random.default_rng(77), ny, nx, 0.06)
     rows, first = pkg.decompose(ny, size)
     r, f = int(rows[rank]), int(first[rank])
     sim = pkg.Simulation.slab(nx, ny, f, r, rank, size, DENSITY, ACCEL, OMEGA, float(pkg.free_cells_inv(obstacles)),
-                              obstacles[f:f + r], device=local)
+                              obstacles[f:f + r], device=local, inplace=inplace)
     blobs = [None] * size
     dist.all_gather_object(blobs, sim.export_ipc())
     sim.connect_ipc(blobs[(rank - 1) % size], blobs[(rank + 1) % size])

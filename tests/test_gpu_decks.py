@@ -109,3 +109,16 @@ def test_final_state_can_be_switched_off(pkg, tmp_path):
                          env={**os.environ, "LBM_FINAL_STATE": "0"})
     assert res.returncode == 0
     assert os.path.exists(tmp_path / "av_vels.dat") and not os.path.exists(tmp_path / "final_state.dat")
+
+
+@pytest.mark.parametrize("gpus", ["1", "3"])
+def test_inplace_through_the_cli(pkg, cli_runs, tmp_path, gpus):
+    """LBM_INPLACE=1 (one population buffer per slab, 40 000 in-place steps, graph replay): the same
+    final_state.dat byte for byte, alone and as three slabs in a ring on device 0."""
+    pfile, ofile = deck_paths("128x128")
+    res = subprocess.run([pkg.EXE_PATH, pfile, ofile], cwd=tmp_path, capture_output=True, text=True,
+                         env={**os.environ, "LBM_INPLACE": "1", "LBM_GPUS": gpus, "LBM_DEVICES": ",".join(["0"] * int(gpus))})
+    assert res.returncode == 0, res.stderr
+    d, _ = cli_runs["128x128"]
+    assert open(tmp_path / "final_state.dat", "rb").read() == open(d / "final_state.dat", "rb").read()
+    assert res.stdout.splitlines()[1].split()[-1] == REF_STRICT["128x128"]["reynolds"]

@@ -21,24 +21,26 @@ def need_gpus(pkg, n):
         pytest.skip(f"needs {n} GPUs, {pkg.device_count()} visible")
 
 
+@pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("n", [2, 4, 8])
-def test_single_process_multi_device(pkg, oracle, n):
+def test_single_process_multi_device(pkg, oracle, n, inplace):
     need_gpus(pkg, n)
     rng = np.random.default_rng(n)
-    nx, ny, iters = 256, 8 * n + 5, 200
+    nx, ny, iters = 256, 8 * n + 5, 201 if inplace else 200       # in place: end in the shifted layout L1
     obstacles = random_obstacles(rng, ny, nx, 0.06)
     cells0 = random_cells(rng, ny, nx)
     ref = cells0.copy()
     ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
-    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n) as sim:
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n, inplace=inplace) as sim:
         sim.set_cells(cells0)
         av = sim.run(iters)
         assert np.array_equal(bits(sim.get_cells()), bits(ref))
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
+@pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("n", [2, 4, 8])
-def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, tmp_path):
+def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
     """torchrun-style launch: n processes, CUDA IPC handles exchanged with torch.distributed."""
     need_gpus(pkg, n)
     with socket.socket() as s:
@@ -48,7 +50,8 @@ def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(out)]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env={**os.environ, "LBM_TEST_INPLACE": "1" if inplace else "0"})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     data = np.load(out)
     obstacles, cells = data["obstacles"], data["cells"]

@@ -303,3 +303,27 @@ def test_inplace_rejects_what_it_cannot_do(pkg):
     with pkg.Simulation(32, 9, DENSITY, ACCEL, OMEGA, np.zeros((9, 32), np.int32), inplace=True) as sim:
         with pytest.raises(pkg.LBMError, match="does not apply"):
             sim.set_option("kernel", 1)
+
+
+@pytest.mark.parametrize("iters", [20, 21])
+@pytest.mark.parametrize("n_slabs,nx,ny", [(2, 128, 16), (3, 136, 19), (4, 256, 31), (8, 128, 24)])
+def test_inplace_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny, iters):
+    """In-place slabs in a ring: the NEIGHBOUR flavour writes into the neighbours' owned edge rows, the LOCAL flavour
+    pushes halo copies; after an odd number of steps the getters decode edge-row populations from the neighbours."""
+    rng = np.random.default_rng(n_slabs * 100 + ny + iters)
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
+    obstacles[:, 0] = rng.random(ny) < 0.5
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs, inplace=True) as sim:
+        assert sim.get_option("launches_per_step") == 1 and sim.get_option("inplace") == 1
+        sim.set_cells(cells0)
+        ref = assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+        for got, want in zip(sim.final_state(), oracle.final_state(ref, obstacles, DENSITY)):
+            assert np.array_equal(bits(got), bits(want))
+        # and on from whichever layout the run ended in
+        ref2 = ref.copy()
+        ref_av, ref_exact = oracle.run(ref2, obstacles, 7, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles), exact=True)
+        av = sim.run(7)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref2))
+        assert_av(av, ref_av, ref_exact)
