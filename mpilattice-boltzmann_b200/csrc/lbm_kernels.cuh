@@ -374,142 +374,33 @@ __device__ __forceinline__ void st3_high(float* p, float4 v)
   *reinterpret_cast<float2*>(p + 2) = make_float2(v.z, v.w);
 }
 
-// PEER = true: a slab of a multi-GPU ring.  As in step_vec4<PEER> the two edge rows are the first work items of
-// the launch and carry the flag handshake.  What crosses the slab boundary:
+// One 128-cell row segment in place.  EDGE = true: an edge row of a ring slab (multi-GPU) -- what crosses the
+// slab boundary:
 //   LOCAL flavour      (-> L0) copies of planes 2,5,6 of the last row go to the northern neighbour's halo row 0 and
 //                      planes 4,7,8 of the first row to the southern neighbour's halo row rows+1 (as step_vec4);
 //   NEIGHBOUR flavour  (-> L1) pulls from the local halo rows, and the values it would write back into a halo row are
 //                      stored straight into the neighbour's OWNED edge row instead (its row `rows` / row 1), which is
 //                      where the neighbour's next LOCAL step reads them -- nobody else touches those slots.
-template <bool NEIGHBOUR, bool PEER, int HINT>
-__device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restrict__ buf, const int accel_row)
+template <bool NEIGHBOUR, bool EDGE, int HINT>
+__device__ __forceinline__ void inplace_segment(const StepArgs& a, float* __restrict__ buf, const int row, const int ch,
+                                                const int accel_row, double& acc)
 {
   const int lane = threadIdx.x & 31;
-  const int warps = blockDim.x >> 5;
-  const long nseg = (long)a.row_count * a.chunks;
   const size_t P = a.plane;
-  double acc = 0.0;
+  const int x0 = ch * kSegCells + lane * 4;
+  const bool active = x0 < a.nx;
+  const size_t o_c = (size_t)row * a.nx;
+  const unsigned bits = active ? ((__ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5)) >> (x0 & 31)) & 0xFu) : 0u;
+  const bool fold_accel = (row == accel_row);
+  float f[4][9];
 
-  for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
-    int row, ch;
-    bool edge = false;
-    if (PEER) {
-      const long e2 = 2L * a.chunks;
-      if (seg < e2) {
-        edge = true;
-        const bool first = seg < a.chunks;
-        row = first ? a.row_first : a.row_last;
-        ch = (int)(first ? seg : seg - a.chunks);
-        warp_peer_wait(a);
-      } else {
-        const long s2 = seg - e2;
-        const int ri = (int)(s2 / a.chunks);
-        ch = (int)(s2 - (long)ri * a.chunks);
-        row = a.row_first + 1 + ri;
-      }
-    } else {
-      const int ri = (int)(seg / a.chunks);
-      ch = (int)(seg - (long)ri * a.chunks);
-      row = a.row_begin + ri * a.row_stride;
-    }
-    const int x0 = ch * kSegCells + lane * 4;
-    const bool active = x0 < a.nx;
-    const size_t o_c = (size_t)row * a.nx;
-    const unsigned bits = active ? ((__ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5)) >> (x0 & 31)) & 0xFu) : 0u;
-    const bool fold_accel = (row == accel_row);
-    float f[4][9];
-
-    if (!NEIGHBOUR) {
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-          const float4 v = ld4_rw<HINT>(buf + (size_t)opposite(k) * P + o_c + x0);
-          f[0][k] = v.x; f[1][k] = v.y; f[2][k] = v.z; f[3][k] = v.w;
-        }
-        float u4 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const bool blocked = (bits >> j) & 1u;
-          const float u = collide(f[j], blocked, a.c.omega);
-          u4 = (j == 0) ? u : add(u4, u);
-          if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-        }
-        acc += (double)u4;
-#pragma unroll
-        for (int k = 0; k < 9; k++)
-          st4_rw<HINT>(buf + (size_t)k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
-        if (PEER) {
-          if (row == a.row_last) {
-            const size_t o = (size_t)a.north_row * a.nx + x0;
-            *reinterpret_cast<float4*>(a.north_dst + 2 * a.north_plane + o) = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
-            *reinterpret_cast<float4*>(a.north_dst + 5 * a.north_plane + o) = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
-            *reinterpret_cast<float4*>(a.north_dst + 6 * a.north_plane + o) = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
-          }
-          if (row == a.row_first) {
-            const size_t o = (size_t)a.south_row * a.nx + x0;
-            *reinterpret_cast<float4*>(a.south_dst + 4 * a.south_plane + o) = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
-            *reinterpret_cast<float4*>(a.south_dst + 7 * a.south_plane + o) = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
-            *reinterpret_cast<float4*>(a.south_dst + 8 * a.south_plane + o) = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
-          }
-        }
-      }
-      if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
-      continue;
-    }
-
-    // ---- NEIGHBOUR flavour: the pull of step_vec4, then the push back into the very same locations ----
-    const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
-    const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
-    const bool west_edge = (lane == 0);
-    const bool east_edge = (lane == 31) || (x0 + 4 >= a.nx);
-    const int xw = (x0 == 0) ? a.nx - 1 : x0 - 1;
-    const int xe = (x0 + 4 >= a.nx) ? 0 : x0 + 4;
-    const size_t o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
-
-    float4 c[9];
-    float w_c = 0.f, w_s = 0.f, w_n = 0.f, e_c = 0.f, e_s = 0.f, e_n = 0.f;
+  if (!NEIGHBOUR) {
     if (active) {
-      c[0] = ld4_rw<HINT>(buf + 0 * P + o_c + x0);
-      c[1] = ld4_rw<HINT>(buf + 1 * P + o_c + x0);
-      c[2] = ld4_rw<HINT>(buf + 2 * P + o_s + x0);
-      c[3] = ld4_rw<HINT>(buf + 3 * P + o_c + x0);
-      c[4] = ld4_rw<HINT>(buf + 4 * P + o_n + x0);
-      c[5] = ld4_rw<HINT>(buf + 5 * P + o_s + x0);
-      c[6] = ld4_rw<HINT>(buf + 6 * P + o_s + x0);
-      c[7] = ld4_rw<HINT>(buf + 7 * P + o_n + x0);
-      c[8] = ld4_rw<HINT>(buf + 8 * P + o_n + x0);
-      if (west_edge) {
-        w_c = ld1_rw<HINT>(buf + 1 * P + o_c + xw);
-        w_s = ld1_rw<HINT>(buf + 5 * P + o_s + xw);
-        w_n = ld1_rw<HINT>(buf + 8 * P + o_n + xw);
-      }
-      if (east_edge) {
-        e_c = ld1_rw<HINT>(buf + 3 * P + o_c + xe);
-        e_s = ld1_rw<HINT>(buf + 6 * P + o_s + xe);
-        e_n = ld1_rw<HINT>(buf + 7 * P + o_n + xe);
-      }
-    } else {
 #pragma unroll
-      for (int k = 0; k < 9; k++) c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
-    const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
-    const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
-    const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
-    const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
-    const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-
-    f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
-    f[0][1] = west_edge ? w_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
-    f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
-    f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = east_edge ? e_c : dn3;
-    f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
-    f[0][5] = west_edge ? w_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
-    f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = east_edge ? e_s : dn6;
-    f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = east_edge ? e_n : dn7;
-    f[0][8] = west_edge ? w_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-
-    if (active) {
+      for (int k = 0; k < 9; k++) {
+        const float4 v = ld4_rw<HINT>(buf + (size_t)opposite(k) * P + o_c + x0);
+        f[0][k] = v.x; f[1][k] = v.y; f[2][k] = v.z; f[3][k] = v.w;
+      }
       float u4 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -519,59 +410,171 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
         if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
       }
       acc += (double)u4;
-    }
-    // the value that belongs to the neighbouring lane's aligned group of four: (slot 1, x-1) <- f3(x) etc.
-    const float g3 = __shfl_down_sync(0xffffffffu, f[0][3], 1);
-    const float g7 = __shfl_down_sync(0xffffffffu, f[0][7], 1);
-    const float g6 = __shfl_down_sync(0xffffffffu, f[0][6], 1);
-    const float g1 = __shfl_up_sync(0xffffffffu, f[3][1], 1);
-    const float g8 = __shfl_up_sync(0xffffffffu, f[3][8], 1);
-    const float g5 = __shfl_up_sync(0xffffffffu, f[3][5], 1);
-    if (active) {
-      // where the rows below / above are written: the rows just read, or (slab edge rows of a ring) the
-      // neighbour's owned edge row over NVLink
-      float* bs = buf; float* bn = buf;
-      size_t Ps = P, Pn = P, w_s_off = o_s, w_n_off = o_n;
-      if (PEER) {
-        if (row == a.row_first) { bs = a.south_dst; Ps = a.south_plane; w_s_off = (size_t)a.south_row * a.nx; }
-        if (row == a.row_last) { bn = a.north_dst; Pn = a.north_plane; w_n_off = (size_t)a.north_row * a.nx; }
-      }
-      st4_rw<HINT>(buf + 0 * P + o_c + x0, make_float4(f[0][0], f[1][0], f[2][0], f[3][0]));
-      st4_rw<HINT>(bs + 2 * Ps + w_s_off + x0, make_float4(f[0][4], f[1][4], f[2][4], f[3][4]));
-      st4_rw<HINT>(bn + 4 * Pn + w_n_off + x0, make_float4(f[0][2], f[1][2], f[2][2], f[3][2]));
-      const float4 v1 = make_float4(f[1][3], f[2][3], f[3][3], g3);   // slot 1, this row
-      const float4 v5 = make_float4(f[1][7], f[2][7], f[3][7], g7);   // slot 5, row below
-      const float4 v8 = make_float4(f[1][6], f[2][6], f[3][6], g6);   // slot 8, row above
-      const float4 v3 = make_float4(g1, f[0][1], f[1][1], f[2][1]);   // slot 3, this row
-      const float4 v6 = make_float4(g8, f[0][8], f[1][8], f[2][8]);   // slot 6, row below
-      const float4 v7 = make_float4(g5, f[0][5], f[1][5], f[2][5]);   // slot 7, row above
-      if (!east_edge) {
-        st4_rw<HINT>(buf + 1 * P + o_c + x0, v1);
-        st4_rw<HINT>(bs + 5 * Ps + w_s_off + x0, v5);
-        st4_rw<HINT>(bn + 8 * Pn + w_n_off + x0, v8);
-      } else {
-        // the fourth element is the next segment's west scalar; this lane's own east scalars go back too
-        st3_low(buf + 1 * P + o_c + x0, v1);
-        st3_low(bs + 5 * Ps + w_s_off + x0, v5);
-        st3_low(bn + 8 * Pn + w_n_off + x0, v8);
-        buf[3 * P + o_c + xe] = f[3][1];
-        bs[6 * Ps + w_s_off + xe] = f[3][8];
-        bn[7 * Pn + w_n_off + xe] = f[3][5];
-      }
-      if (!west_edge) {
-        st4_rw<HINT>(buf + 3 * P + o_c + x0, v3);
-        st4_rw<HINT>(bs + 6 * Ps + w_s_off + x0, v6);
-        st4_rw<HINT>(bn + 7 * Pn + w_n_off + x0, v7);
-      } else {
-        st3_high(buf + 3 * P + o_c + x0, v3);
-        st3_high(bs + 6 * Ps + w_s_off + x0, v6);
-        st3_high(bn + 7 * Pn + w_n_off + x0, v7);
-        buf[1 * P + o_c + xw] = f[0][3];
-        bs[5 * Ps + w_s_off + xw] = f[0][7];
-        bn[8 * Pn + w_n_off + xw] = f[0][6];
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        st4_rw<HINT>(buf + (size_t)k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+      if (EDGE) {
+        if (row == a.row_last) {
+          const size_t o = (size_t)a.north_row * a.nx + x0;
+          *reinterpret_cast<float4*>(a.north_dst + 2 * a.north_plane + o) = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
+          *reinterpret_cast<float4*>(a.north_dst + 5 * a.north_plane + o) = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
+          *reinterpret_cast<float4*>(a.north_dst + 6 * a.north_plane + o) = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
+        }
+        if (row == a.row_first) {
+          const size_t o = (size_t)a.south_row * a.nx + x0;
+          *reinterpret_cast<float4*>(a.south_dst + 4 * a.south_plane + o) = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
+          *reinterpret_cast<float4*>(a.south_dst + 7 * a.south_plane + o) = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
+          *reinterpret_cast<float4*>(a.south_dst + 8 * a.south_plane + o) = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
+        }
       }
     }
-    if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
+    return;
+  }
+
+  // ---- NEIGHBOUR flavour: the pull of step_vec4, then the push back into the very same locations ----
+  const int rs = (row == a.row_first) ? a.south_of_first : row - 1;
+  const int rn = (row == a.row_last) ? a.north_of_last : row + 1;
+  const bool west_edge = (lane == 0);
+  const bool east_edge = (lane == 31) || (x0 + 4 >= a.nx);
+  const int xw = (x0 == 0) ? a.nx - 1 : x0 - 1;
+  const int xe = (x0 + 4 >= a.nx) ? 0 : x0 + 4;
+  const size_t o_s = (size_t)rs * a.nx, o_n = (size_t)rn * a.nx;
+
+  float4 c[9];
+  float w_c = 0.f, w_s = 0.f, w_n = 0.f, e_c = 0.f, e_s = 0.f, e_n = 0.f;
+  if (active) {
+    c[0] = ld4_rw<HINT>(buf + 0 * P + o_c + x0);
+    c[1] = ld4_rw<HINT>(buf + 1 * P + o_c + x0);
+    c[2] = ld4_rw<HINT>(buf + 2 * P + o_s + x0);
+    c[3] = ld4_rw<HINT>(buf + 3 * P + o_c + x0);
+    c[4] = ld4_rw<HINT>(buf + 4 * P + o_n + x0);
+    c[5] = ld4_rw<HINT>(buf + 5 * P + o_s + x0);
+    c[6] = ld4_rw<HINT>(buf + 6 * P + o_s + x0);
+    c[7] = ld4_rw<HINT>(buf + 7 * P + o_n + x0);
+    c[8] = ld4_rw<HINT>(buf + 8 * P + o_n + x0);
+    if (west_edge) {
+      w_c = ld1_rw<HINT>(buf + 1 * P + o_c + xw);
+      w_s = ld1_rw<HINT>(buf + 5 * P + o_s + xw);
+      w_n = ld1_rw<HINT>(buf + 8 * P + o_n + xw);
+    }
+    if (east_edge) {
+      e_c = ld1_rw<HINT>(buf + 3 * P + o_c + xe);
+      e_s = ld1_rw<HINT>(buf + 6 * P + o_s + xe);
+      e_n = ld1_rw<HINT>(buf + 7 * P + o_n + xe);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+  const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+  const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+  const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+  const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+  const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+
+  f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+  f[0][1] = west_edge ? w_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+  f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+  f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = east_edge ? e_c : dn3;
+  f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+  f[0][5] = west_edge ? w_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+  f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = east_edge ? e_s : dn6;
+  f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = east_edge ? e_n : dn7;
+  f[0][8] = west_edge ? w_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+
+  if (active) {
+    float u4 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool blocked = (bits >> j) & 1u;
+      const float u = collide(f[j], blocked, a.c.omega);
+      u4 = (j == 0) ? u : add(u4, u);
+      if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+    }
+    acc += (double)u4;
+  }
+  // the value that belongs to the neighbouring lane's aligned group of four: (slot 1, x-1) <- f3(x) etc.
+  const float g3 = __shfl_down_sync(0xffffffffu, f[0][3], 1);
+  const float g7 = __shfl_down_sync(0xffffffffu, f[0][7], 1);
+  const float g6 = __shfl_down_sync(0xffffffffu, f[0][6], 1);
+  const float g1 = __shfl_up_sync(0xffffffffu, f[3][1], 1);
+  const float g8 = __shfl_up_sync(0xffffffffu, f[3][8], 1);
+  const float g5 = __shfl_up_sync(0xffffffffu, f[3][5], 1);
+  if (active) {
+    // where the rows below / above are written: the rows just read, or (slab edge rows of a ring) the
+    // neighbour's owned edge row over NVLink
+    float* bs = buf; float* bn = buf;
+    size_t Ps = P, Pn = P, w_s_off = o_s, w_n_off = o_n;
+    if (EDGE) {
+      if (row == a.row_first) { bs = a.south_dst; Ps = a.south_plane; w_s_off = (size_t)a.south_row * a.nx; }
+      if (row == a.row_last) { bn = a.north_dst; Pn = a.north_plane; w_n_off = (size_t)a.north_row * a.nx; }
+    }
+    st4_rw<HINT>(buf + 0 * P + o_c + x0, make_float4(f[0][0], f[1][0], f[2][0], f[3][0]));
+    st4_rw<HINT>(bs + 2 * Ps + w_s_off + x0, make_float4(f[0][4], f[1][4], f[2][4], f[3][4]));
+    st4_rw<HINT>(bn + 4 * Pn + w_n_off + x0, make_float4(f[0][2], f[1][2], f[2][2], f[3][2]));
+    const float4 v1 = make_float4(f[1][3], f[2][3], f[3][3], g3);   // slot 1, this row
+    const float4 v5 = make_float4(f[1][7], f[2][7], f[3][7], g7);   // slot 5, row below
+    const float4 v8 = make_float4(f[1][6], f[2][6], f[3][6], g6);   // slot 8, row above
+    const float4 v3 = make_float4(g1, f[0][1], f[1][1], f[2][1]);   // slot 3, this row
+    const float4 v6 = make_float4(g8, f[0][8], f[1][8], f[2][8]);   // slot 6, row below
+    const float4 v7 = make_float4(g5, f[0][5], f[1][5], f[2][5]);   // slot 7, row above
+    if (!east_edge) {
+      st4_rw<HINT>(buf + 1 * P + o_c + x0, v1);
+      st4_rw<HINT>(bs + 5 * Ps + w_s_off + x0, v5);
+      st4_rw<HINT>(bn + 8 * Pn + w_n_off + x0, v8);
+    } else {
+      // the fourth element is the next segment's west scalar; this lane's own east scalars go back too
+      st3_low(buf + 1 * P + o_c + x0, v1);
+      st3_low(bs + 5 * Ps + w_s_off + x0, v5);
+      st3_low(bn + 8 * Pn + w_n_off + x0, v8);
+      buf[3 * P + o_c + xe] = f[3][1];
+      bs[6 * Ps + w_s_off + xe] = f[3][8];
+      bn[7 * Pn + w_n_off + xe] = f[3][5];
+    }
+    if (!west_edge) {
+      st4_rw<HINT>(buf + 3 * P + o_c + x0, v3);
+      st4_rw<HINT>(bs + 6 * Ps + w_s_off + x0, v6);
+      st4_rw<HINT>(bn + 7 * Pn + w_n_off + x0, v7);
+    } else {
+      st3_high(buf + 3 * P + o_c + x0, v3);
+      st3_high(bs + 6 * Ps + w_s_off + x0, v6);
+      st3_high(bn + 7 * Pn + w_n_off + x0, v7);
+      buf[1 * P + o_c + xw] = f[0][3];
+      bs[5 * Ps + w_s_off + xw] = f[0][7];
+      bn[8 * Pn + w_n_off + xw] = f[0][6];
+    }
+  }
+}
+
+// PEER = true: a slab of a multi-GPU ring.  As in step_vec4<PEER> the two edge rows are the first work items of
+// the launch and carry the flag handshake; the interior rows run the same code as a single-GPU launch.
+template <bool NEIGHBOUR, bool PEER, int HINT>
+__device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restrict__ buf, const int accel_row)
+{
+  const int warps = blockDim.x >> 5;
+  const long nseg = (long)a.row_count * a.chunks;
+  double acc = 0.0;
+
+  for (long seg = (long)blockIdx.x * warps + (threadIdx.x >> 5); seg < nseg; seg += (long)gridDim.x * warps) {
+    if (PEER) {
+      const long e2 = 2L * a.chunks;
+      if (seg < e2) {
+        const bool first = seg < a.chunks;
+        warp_peer_wait(a);
+        inplace_segment<NEIGHBOUR, true, HINT>(a, buf, first ? a.row_first : a.row_last, (int)(first ? seg : seg - a.chunks),
+                                               accel_row, acc);
+        warp_peer_signal(a, 2u * (unsigned)a.chunks);
+      } else {
+        const long s2 = seg - e2;
+        const int ri = (int)(s2 / a.chunks);
+        inplace_segment<NEIGHBOUR, false, HINT>(a, buf, a.row_first + 1 + ri, (int)(s2 - (long)ri * a.chunks), accel_row, acc);
+      }
+    } else {
+      const int ri = (int)(seg / a.chunks);
+      inplace_segment<NEIGHBOUR, false, HINT>(a, buf, a.row_begin + ri * a.row_stride, (int)(seg - (long)ri * a.chunks),
+                                              accel_row, acc);
+    }
   }
   return acc;
 }

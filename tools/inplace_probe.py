@@ -10,8 +10,12 @@ import __graft_entry__ as entry  # noqa: E402
 pkg = entry.load_package()
 nx = ny = int(os.environ.get("N", 16384))
 steps = int(os.environ.get("STEPS", 6))
-with pkg.Simulation(nx, ny, 0.1, 0.005, 1.85, pkg.decks.channel_obstacles(nx, ny), inplace=bool(int(os.environ.get("INPLACE", 1)))) as sim:
+slabs = int(os.environ.get("SLABS", 1))
+with pkg.Simulation(nx, ny, 0.1, 0.005, 1.85, pkg.decks.channel_obstacles(nx, ny), n_slabs=slabs, devices=[0] * slabs,
+                    inplace=bool(int(os.environ.get("INPLACE", 1)))) as sim:
     sim.set_option("graph_steps", 0)
     sim.enqueue(steps)
     sim.sync()
-    print("ms per step", sim.elapsed_ms() / steps)
+    sim.enqueue(steps)
+    sim.sync()
+    print("slabs", slabs, "inplace", sim.get_option("inplace"), "ms per step", sim.elapsed_ms() / steps)
