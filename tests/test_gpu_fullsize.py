@@ -118,3 +118,39 @@ def test_synthetic_deck_through_the_cli(pkg, oracle, tmp_path):
     reynolds = float(res.stdout.splitlines()[1].split()[-1])
     ref_re = float(oracle.reynolds(cells, narrow, pkg.free_cells_inv(narrow), OMEGA, 10))
     assert abs(reynolds - ref_re) / ref_re < 5e-2
+
+
+def _enough_memory(host_gb, device_gb):
+    import psutil
+    import torch
+    return psutil.virtual_memory().available > host_gb * 2**30 and torch.cuda.mem_get_info()[0] > device_gb * 2**30
+
+
+@pytest.mark.parametrize("inplace,ny", [(False, 65536 + 4), (True, 131072 + 4)])
+def test_maximum_sizes_index_arithmetic(pkg, oracle, inplace, ny):
+    """Grids whose element offsets leave 32 bits: ping-pong 16384 x 65540 (9 planes of 2^30 floats, 77 GB for the
+    pair) and in place 16384 x 131076 (planes of more than 2^31 floats, 77 GB) -- pressure of every cell against the
+    tiled 128-wide oracle after 3 steps (in place: the shifted layout L1, read through the staging buffer)."""
+    import ctypes
+    host_gb = 4.0 * NX * ny * 2 / 2**30 + 8
+    if not _enough_memory(host_gb, 80):
+        pytest.skip("needs ~%d GB of host memory and 80 GB of device memory" % host_gb)
+    period, iters = 128, 3
+    narrow = np.zeros((ny, period), np.int32)
+    narrow[0, :] = narrow[-1, :] = 1
+    narrow[ny // 2, 5:9] = 1                       # something that is not x-invariant, far from the start of the planes
+    narrow[ny - 3, 100:103] = 1
+    cells = oracle.init_cells(period, ny, DENSITY)
+    _, av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow), exact=True)
+    ref_pressure = oracle.final_state(cells, narrow, DENSITY)[3]
+    obstacles = np.tile(narrow, (1, NX // period))
+    with pkg.Simulation(NX, ny, DENSITY, ACCEL, OMEGA, obstacles, inplace=inplace) as sim:
+        del obstacles
+        av = sim.run(iters)
+        pressure = np.empty((ny, NX), np.float32)
+        rc = pkg.library().lbm_b200_get_final_state(sim._h, None, None, None, pressure.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert rc == 0
+    assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
+    for y0 in range(0, ny, 8192):                  # compare in bands: no second full-size temporary
+        band = slice(y0, min(ny, y0 + 8192))
+        assert np.array_equal(bits(pressure[band]), bits(np.tile(ref_pressure[band], (1, NX // period)))), f"rows {band}"
