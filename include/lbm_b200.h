@@ -157,8 +157,9 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
  *   "resident"      1 = run up to 256 timesteps per cooperative launch with a grid-wide barrier between
  *                   steps (for launch-latency-bound grids), 0 = never, -1 = automatic (single-GPU grids of
  *                   up to 2^22 cells)
- *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches, -1 = automatic:
- *                   graphs of 256 steps for single-GPU grids of up to 2^22 cells)
+ *   "graph_steps"   timesteps per CUDA-graph launch (0 = plain launches, -1 = automatic: graphs of 256 steps
+ *                   for grids of up to 2^22 cells per GPU).  Ring slabs replay one independent graph per device:
+ *                   their kernels are ordered by the flag words they exchange, not by stream dependencies
  *   "ctas_per_sm"   persistent-grid size in CTAs per SM (0 = occupancy query)
  *   "min_ctas"      register budget of the 128-bit kernel: 2, 3 or 4 resident CTAs per SM
  *   "cache_hint"    0 = read-only loads + plain stores, 1 = streaming loads and stores,

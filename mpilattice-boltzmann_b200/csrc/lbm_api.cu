@@ -242,8 +242,11 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
     if (e != cudaSuccess)
       return fail(LBM_B200_ERR_ALLOC, "cudaMalloc of %zu bytes for populations failed: %s", bytes, cudaGetErrorString(e));
   }
-  CUDA_TRY(cudaMalloc(&s.flags, kFlagWords * sizeof(unsigned)));
-  CUDA_TRY(cudaMemset(s.flags, 0, kFlagWords * sizeof(unsigned)));
+  // flag words: kFlagWords for the slab-level handshake, then one per 128-cell chunk from the south and one per
+  // chunk from the north (csrc/lbm_kernels.cuh, warp_peer_wait)
+  const size_t flag_words = kFlagWords + 2 * (size_t)((h->nx + lbm::kSegCells - 1) / lbm::kSegCells);
+  CUDA_TRY(cudaMalloc(&s.flags, flag_words * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.flags, 0, flag_words * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&s.cursor, sizeof(unsigned)));
   CUDA_TRY(cudaMemset(s.cursor, 0, sizeof(unsigned)));
   CUDA_TRY(cudaEventCreate(&s.ev_start));
@@ -371,10 +374,17 @@ void peer_args(const lbm_b200* h, const Slab& s, StepArgs& a)
     a.south_dst = s.south.buf[0];
     if (h->cur == 0) { a.north_row = 1; a.south_row = s.south.rows; }
   }
-  a.wait_from_south = s.flags + kFromSouth;
-  a.wait_from_north = s.flags + kFromNorth;
-  a.signal_north = s.north.flags + kFromSouth;     // I am my northern neighbour's south
-  a.signal_south = s.south.flags + kFromNorth;
+  if (use_vec4(h)) {                               // one flag word per 128-cell chunk of the edge rows
+    a.wait_from_south = s.flags + kFlagWords;
+    a.wait_from_north = s.flags + kFlagWords + a.chunks;
+    a.signal_north = s.north.flags + kFlagWords;   // I am my northern neighbour's south
+    a.signal_south = s.south.flags + kFlagWords + a.chunks;
+  } else {
+    a.wait_from_south = s.flags + kFromSouth;
+    a.wait_from_north = s.flags + kFromNorth;
+    a.signal_north = s.north.flags + kFromSouth;
+    a.signal_south = s.south.flags + kFromNorth;
+  }
   a.epoch = s.flags + kEpoch;
   a.done = s.flags + kDone;
 }
@@ -493,32 +503,65 @@ int enqueue_reduce(lbm_b200* h, int steps)
   return LBM_B200_OK;
 }
 
-// Captures `len` steps (+ their reduce) into one CUDA graph per slab, for both buffer parities.
+// Captures `len` steps (+ their reduce) into one CUDA graph per stream, for both buffer parities.  Slabs of a
+// ring are ordered by the flag words their kernels exchange, not by stream dependencies, so every stream
+// (device) gets its own independent graph and the host launches one graph per device and `len` steps.
 int build_graphs(lbm_b200* h, int len)
 {
   destroy_graphs(h);
-  if (h->slabs.size() != 1 || h->n_ranks != 1)
-    return fail(LBM_B200_ERR_STATE, "graph_steps is supported for single-slab handles only");
-  Slab& s = h->slabs[0];
-  CUDA_TRY(cudaSetDevice(s.device));
   const int cur0 = h->cur;
-  s.graphs.assign(2, nullptr);
+  for (Slab& s : h->slabs) s.graphs.assign(2, nullptr);
   for (int parity = 0; parity < 2; parity++) {
     h->cur = parity;
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
     int rc = LBM_B200_OK;
+    size_t begun = 0;
+    for (; begun < h->slabs.size() && rc == LBM_B200_OK; begun++) {
+      Slab& s = h->slabs[begun];
+      if (!s.own_stream) continue;
+      if (cudaSetDevice(s.device) != cudaSuccess || cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        rc = fail(LBM_B200_ERR_CUDA, "graph capture could not begin: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc != LBM_B200_OK) begun--;                  // the slab that failed has no capture to end
     for (int t = 0; t < len && rc == LBM_B200_OK; t++) rc = enqueue_step(h, t, true);
     if (rc == LBM_B200_OK) rc = enqueue_reduce(h, len);
-    cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
-    if (rc != LBM_B200_OK) { if (graph) cudaGraphDestroy(graph); h->cur = cur0; return rc; }
-    if (e != cudaSuccess) { h->cur = cur0; return fail(LBM_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e)); }
-    e = cudaGraphInstantiate(&s.graphs[parity], graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { h->cur = cur0; return fail(LBM_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    for (size_t i = 0; i < begun; i++) {
+      Slab& s = h->slabs[i];
+      if (!s.own_stream) continue;
+      cudaGraph_t graph = nullptr;
+      cudaSetDevice(s.device);
+      cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+      if (e != cudaSuccess && rc == LBM_B200_OK) rc = fail(LBM_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      if (rc == LBM_B200_OK) {
+        e = cudaGraphInstantiate(&s.graphs[parity], graph, 0);
+        if (e != cudaSuccess) rc = fail(LBM_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();
+    if (rc != LBM_B200_OK) { h->cur = cur0; destroy_graphs(h); return rc; }
   }
   h->cur = cur0;
   h->graph_len = len;
+  return LBM_B200_OK;
+}
+
+// The slab-level (scalar kernel) and chunk-level (128-bit kernels) handshakes keep separate flag words but share
+// the epoch: after switching kernels on a ring, every flag word is brought up to the slab's epoch.  The caller
+// has drained the streams.
+int resync_flags(lbm_b200* h)
+{
+  if (h->n_ranks == 1) return LBM_B200_OK;
+  const size_t words = kFlagWords + 2 * (size_t)((h->nx + lbm::kSegCells - 1) / lbm::kSegCells);
+  std::vector<unsigned> host(words);
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    unsigned epoch = 0;
+    CUDA_TRY(cudaMemcpy(&epoch, s.flags + kEpoch, sizeof epoch, cudaMemcpyDeviceToHost));
+    std::fill(host.begin(), host.end(), epoch);
+    host[kDone] = 0;
+    for (int i = kDone + 1; i < kFlagWords; i++) host[i] = 0;
+    CUDA_TRY(cudaMemcpy(s.flags, host.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   return LBM_B200_OK;
 }
 
@@ -831,7 +874,9 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
   if (glen < 0) {
     // auto: grids whose step kernel is launch-latency bound (a few microseconds) are replayed
     // from CUDA graphs -- measured 4.1 -> 2.7 us per step on the 128..256-wide decks
-    const bool small = h->slabs.size() == 1 && h->n_ranks == 1 && (long)h->nx * h->ny <= kGraphAutoCells;
+    // (per GPU: a ring slab of a small grid is even more launch bound, and one host thread may be feeding
+    // several devices)
+    const bool small = (long)h->nx * h->ny / h->n_ranks <= kGraphAutoCells;
     glen = (small && iters > 2 * kChunkSteps) ? kChunkSteps : 0;
   }
   if (glen > 0) {
@@ -882,10 +927,14 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       }
     }
     if (glen >= 2 && h->graph_len == glen) {
-      Slab& s = h->slabs[0];
       while (iters - 1 - t >= glen) {                // the very last step never folds a force in
-        CUDA_TRY(cudaGraphLaunch(s.graphs[h->cur], s.stream));
-        h->launches += glen + 2;
+        for (Slab& s : h->slabs) {
+          if (s.own_stream) {
+            CUDA_TRY(cudaSetDevice(s.device));
+            CUDA_TRY(cudaGraphLaunch(s.graphs[h->cur], s.stream));
+          }
+          h->launches += (long)glen * ((h->n_ranks == 1 || use_vec4(h)) ? 1 : 2) + 2;
+        }
         t += glen;
       }
     }
@@ -1088,6 +1137,10 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   lbm_b200_sync(h);
   destroy_graphs(h);
   plan(h);
+  if (!strcmp(key, "kernel")) {
+    int rc = resync_flags(h);
+    if (rc) return rc;
+  }
   return ensure_partials(h);
 }
 

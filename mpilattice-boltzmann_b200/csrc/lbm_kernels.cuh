@@ -35,8 +35,10 @@ struct StepArgs {
   // ---- halo exchange over peer memory (used only by the <PEER> instantiations) ----
   float* north_dst; size_t north_plane; int north_row;   // planes 2,5,6 of row_last  -> neighbour row north_row
   float* south_dst; size_t south_plane; int south_row;   // planes 4,7,8 of row_first -> neighbour row south_row
-  const unsigned* wait_from_south; const unsigned* wait_from_north;   // local flag words the neighbours write
-  unsigned* signal_north; unsigned* signal_south;                     // the neighbours' flag words (peer memory)
+  // local flag words the neighbours write / the neighbours' flag words (peer memory): one word per slab for the
+  // scalar kernel's launch-level handshake, one word per 128-cell chunk for the 128-bit kernels
+  const unsigned* wait_from_south; const unsigned* wait_from_north;
+  unsigned* signal_north; unsigned* signal_south;
   unsigned* epoch;           // local: number of states this slab has published
   unsigned* done;            // local: CTA completion counter of this launch
 };
@@ -84,31 +86,45 @@ __device__ __forceinline__ void peer_signal(const StepArgs& a)
   }
 }
 
-// Warp-granular versions for the 128-bit kernel, where the edge-row segments are the first work items of
-// the SAME launch as the interior: only the warps that own an edge segment wait, and the warp that
-// completes the last of the `total` edge segments publishes the epoch.
-__device__ __forceinline__ void warp_peer_wait(const StepArgs& a)
+// Segment-granular versions for the 128-bit kernels, where the edge-row segments are the first work items of
+// the SAME launch as the interior.  Every 128-cell chunk of an edge row has its own flag word in the neighbour:
+//   * the warp that owns chunk c of the first (last) row waits until the southern (northern) neighbour has
+//     published chunks c-1, c, c+1 (periodic) of the state it is about to read -- the two extra chunks supply the
+//     scalars that cross the segment ends, and the same three flags say that the neighbour is done reading the
+//     halo chunk this warp is about to overwrite;
+//   * after its stores one system-scope fence and ONE flag store publish the chunk -- no counter, no "last warp",
+//     so the exchange latency per step is one fence plus one NVLink hop.
+// The epoch (number of states this slab has published) advances once per launch, by the last CTA to leave.
+__device__ __forceinline__ void warp_peer_wait(const StepArgs& a, bool first, int ch)
 {
-  if ((threadIdx.x & 31) == 0) {
+  const int lane = threadIdx.x & 31;
+  if (lane < 3) {
+    int c = ch - 1 + lane;
+    if (c < 0) c = a.chunks - 1; else if (c >= a.chunks) c = 0;
+    const unsigned* p = (first ? a.wait_from_south : a.wait_from_north) + c;
     const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
-    while ((int)(ld_acquire_sys(a.wait_from_south) - need) < 0) __nanosleep(20);
-    while ((int)(ld_acquire_sys(a.wait_from_north) - need) < 0) __nanosleep(20);
+    while ((int)(ld_acquire_sys(p) - need) < 0) __nanosleep(20);
   }
   __syncwarp();
 }
-__device__ __forceinline__ void warp_peer_signal(const StepArgs& a, unsigned total)
+__device__ __forceinline__ void warp_peer_signal(const StepArgs& a, bool first, int ch)
 {
   __threadfence_system();
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
+    const unsigned next = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
+    st_release_sys((first ? a.signal_south : a.signal_north) + ch, next);
+  }
+}
+// end of a ring launch: the last CTA to leave advances the epoch (device scope: only this slab reads it)
+__device__ __forceinline__ void peer_advance_epoch(const StepArgs& a)
+{
+  if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned prev = atomicAdd(a.done, 1u);
-    if (prev == total - 1) {
+    if (prev == gridDim.x - 1) {
       *a.done = 0;
-      __threadfence_system();
-      const unsigned next = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
-      st_release_sys(a.signal_north, next);
-      st_release_sys(a.signal_south, next);
-      *reinterpret_cast<volatile unsigned*>(a.epoch) = next;
+      *reinterpret_cast<volatile unsigned*>(a.epoch) = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
     }
   }
 }
@@ -189,7 +205,7 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
         const bool first = seg < a.chunks;
         row = first ? a.row_first : a.row_last;
         ch = (int)(first ? seg : seg - a.chunks);
-        warp_peer_wait(a);
+        warp_peer_wait(a, first, ch);
       } else {
         const long s2 = seg - e2;
         const int ri = (int)(s2 / a.chunks);
@@ -311,7 +327,7 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
         }
       }
     }
-    if (PEER && edge) warp_peer_signal(a, 2u * (unsigned)a.chunks);
+    if (PEER && edge) warp_peer_signal(a, row == a.row_first, ch);
   }
 
   return acc;
@@ -325,6 +341,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) step_vec4(const StepArgs a)
 {
   const double acc = vec4_pass<PEER, PEER ? 3 : HINT>(a, a.src, a.dst, a.accel_row);
   block_sum_to(acc, a.partials + blockIdx.x);
+  if (PEER) peer_advance_epoch(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -561,10 +578,10 @@ __device__ __forceinline__ double inplace_pass(const StepArgs& a, float* __restr
       const long e2 = 2L * a.chunks;
       if (seg < e2) {
         const bool first = seg < a.chunks;
-        warp_peer_wait(a);
-        inplace_segment<NEIGHBOUR, true, HINT>(a, buf, first ? a.row_first : a.row_last, (int)(first ? seg : seg - a.chunks),
-                                               accel_row, acc);
-        warp_peer_signal(a, 2u * (unsigned)a.chunks);
+        const int ch = (int)(first ? seg : seg - a.chunks);
+        warp_peer_wait(a, first, ch);
+        inplace_segment<NEIGHBOUR, true, HINT>(a, buf, first ? a.row_first : a.row_last, ch, accel_row, acc);
+        warp_peer_signal(a, first, ch);
       } else {
         const long s2 = seg - e2;
         const int ri = (int)(s2 / a.chunks);
@@ -585,6 +602,7 @@ __global__ void __launch_bounds__(256, 2) step_inplace(const StepArgs a)
 {
   const double acc = inplace_pass<NEIGHBOUR, PEER, PEER ? 0 : HINT>(a, a.dst, a.accel_row);
   block_sum_to(acc, a.partials + blockIdx.x);
+  if (PEER) peer_advance_epoch(a);
 }
 
 // Where the canonical population k of the cell (x, padded row) lives: in place (odd = 0: layout L0), or

@@ -327,3 +327,48 @@ def test_inplace_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny, ite
         av = sim.run(7)
         assert np.array_equal(bits(sim.get_cells()), bits(ref2))
         assert_av(av, ref_av, ref_exact)
+
+
+@pytest.mark.parametrize("inplace", [False, True])
+@pytest.mark.parametrize("n_slabs,kernel", [(3, 2), (2, 1)])
+def test_ring_slabs_replayed_from_graphs(pkg, oracle, n_slabs, kernel, inplace):
+    """CUDA-graph replay of a ring: one graph per stream holds `graph_steps` steps of every slab on it (the flag
+    handshake lives in device memory, so a replay is as good as the launches it recorded).  37 steps in chunks of 8
+    plus a plain tail, then the automatic choice over 600 steps."""
+    if inplace and kernel == 1:
+        pytest.skip("in-place streaming has no one-cell-per-thread kernel")
+    rng = np.random.default_rng(n_slabs * 7 + kernel)
+    nx, ny = 136, 25
+    obstacles = random_obstacles(rng, ny, nx, 0.08)
+    cells0 = random_cells(rng, ny, nx)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs, inplace=inplace) as sim:
+        if not inplace:
+            sim.set_option("kernel", kernel)
+        sim.set_option("graph_steps", 8)
+        sim.set_cells(cells0)
+        ref = assert_parity(sim, oracle, pkg, cells0, obstacles, 37)
+        sim.set_option("graph_steps", -1)
+        ref2 = ref.copy()
+        ref_av, ref_exact = oracle.run(ref2, obstacles, 600, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles), exact=True)
+        av = sim.run(600)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref2))
+        assert_av(av, ref_av, ref_exact)
+        assert sim.get_option("launches") >= 600
+
+
+def test_switching_kernels_on_a_ring_keeps_the_handshake_consistent(pkg, oracle):
+    """The scalar kernel (slab-level flags) and the 128-bit kernel (one flag per 128-cell chunk) share the epoch."""
+    rng = np.random.default_rng(77)
+    nx, ny, n_slabs = 256, 22, 3
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, 15)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        sim.set_cells(cells0)
+        av = [sim.run(4)]
+        sim.set_option("kernel", 1)
+        av.append(sim.run(5))
+        sim.set_option("kernel", 2)
+        av.append(sim.run(6))
+        assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
+        assert_av(np.concatenate(av), ref_av, ref_exact)
