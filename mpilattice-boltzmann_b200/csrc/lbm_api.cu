@@ -524,18 +524,24 @@ int build_graphs(lbm_b200* h, int len)
     if (rc != LBM_B200_OK) begun--;                  // the slab that failed has no capture to end
     for (int t = 0; t < len && rc == LBM_B200_OK; t++) rc = enqueue_step(h, t, true);
     if (rc == LBM_B200_OK) rc = enqueue_reduce(h, len);
+    // end every capture first: nothing may be instantiated while a stream of this thread still captures
+    std::vector<cudaGraph_t> captured(h->slabs.size(), nullptr);
     for (size_t i = 0; i < begun; i++) {
       Slab& s = h->slabs[i];
       if (!s.own_stream) continue;
-      cudaGraph_t graph = nullptr;
       cudaSetDevice(s.device);
-      cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+      cudaError_t e = cudaStreamEndCapture(s.stream, &captured[i]);
       if (e != cudaSuccess && rc == LBM_B200_OK) rc = fail(LBM_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    }
+    for (size_t i = 0; i < begun; i++) {
+      Slab& s = h->slabs[i];
+      if (!captured[i]) continue;
+      cudaSetDevice(s.device);
       if (rc == LBM_B200_OK) {
-        e = cudaGraphInstantiate(&s.graphs[parity], graph, 0);
+        cudaError_t e = cudaGraphInstantiate(&s.graphs[parity], captured[i], 0);
         if (e != cudaSuccess) rc = fail(LBM_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
       }
-      if (graph) cudaGraphDestroy(graph);
+      cudaGraphDestroy(captured[i]);
     }
     cudaGetLastError();
     if (rc != LBM_B200_OK) { h->cur = cur0; destroy_graphs(h); return rc; }

@@ -39,6 +39,27 @@ def test_single_process_multi_device(pkg, oracle, n, inplace):
 
 
 @pytest.mark.parametrize("inplace", [False, True])
+@pytest.mark.parametrize("n", [2, 8])
+def test_graph_replay_across_devices(pkg, oracle, n, inplace):
+    """One independent CUDA graph per device, ordered only by the flag words the kernels exchange over NVLink."""
+    need_gpus(pkg, n)
+    rng = np.random.default_rng(40 + n)
+    nx, ny, iters = 384, 6 * n + 4, 1500                          # automatic choice: 256-step graphs
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    ref_av = oracle.run(ref, obstacles, iters + 45, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n, inplace=inplace) as sim:
+        sim.set_cells(cells0)
+        av = sim.run(iters)
+        assert sim.get_option("launches") > iters
+        sim.set_option("graph_steps", 8)
+        av = np.concatenate([av, sim.run(45)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
+@pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("n", [2, 4, 8])
 def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
     """torchrun-style launch: n processes, CUDA IPC handles exchanged with torch.distributed."""
