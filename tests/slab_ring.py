@@ -56,7 +56,98 @@ def run_slab(pkg, oracle, rank, size, nx, ny, iters, density, accel, omega, obst
     return a[1:rows + 1].copy(), av
 
 
-def worker(rank, size, port, args, out_queue):
+# ---- the in-place (AA access pattern) ring: one buffer per slab, csrc/lbm_kernels.cuh kernel 4 ---------------------
+CX = [0, 1, 0, -1, 0, 1, -1, -1, 1]       # lattice directions of the reference's speed order (d2q9-bgk.c:7-13)
+CY = [0, 0, 1, 0, -1, 1, 1, -1, -1]
+OPP = [0, 3, 4, 1, 2, 7, 8, 5, 6]
+
+
+def swap_rows(up, down, rank, size):
+    """Sends `up` to the northern neighbour and `down` to the southern one; returns (from_south, from_north)."""
+    south, north = (rank - 1) % size, (rank + 1) % size
+    up, down = torch.from_numpy(np.ascontiguousarray(up)), torch.from_numpy(np.ascontiguousarray(down))
+    from_south, from_north = torch.empty_like(up), torch.empty_like(down)
+    ops = [dist.P2POp(dist.isend, up, north, tag=3), dist.P2POp(dist.isend, down, south, tag=4),
+           dist.P2POp(dist.irecv, from_south, south, tag=3), dist.P2POp(dist.irecv, from_north, north, tag=4)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return from_south.numpy(), from_north.numpy()
+
+
+def run_slab_inplace(pkg, oracle, rank, size, nx, ny, iters, density, accel, omega, obstacles, cells0):
+    """The in-place protocol of the product, step for step, with ONE array per slab:
+      NEIGHBOUR step (layout L0 -> L1): pull through the halo rows; population opp(i) goes back to (slot i, cell - c_i);
+          what would land in a halo row is sent into the neighbour's OWNED edge row instead;
+      LOCAL step (L1 -> L0): population j of a cell is in its own slot opp(j); afterwards the usual 3-plane halo push.
+    Returns (this slab's final canonical rows, av_vels partial)."""
+    rows_all, first_all = pkg.decompose(ny, size)
+    rows, first = int(rows_all[rank]), int(first_all[rank])
+    inv = pkg.free_cells_inv(obstacles)
+    buf = np.full((rows + 2, nx, 9), np.nan, np.float32)
+    buf[1:rows + 1] = cells0[first:first + rows]
+    tmp = np.full_like(buf, np.nan)
+    ob = np.zeros((rows + 2, nx), np.int32)
+    ob[1:rows + 1] = obstacles[first:first + rows]
+    accel_row = ny - 2 - first + 1 if first <= ny - 2 < first + rows else -1
+    av = np.zeros(iters, np.float32)
+    exchange_halos(buf, rank, size)
+    odd = 0
+
+    def canonical_row(r):
+        """populations of row r (an interior row) in the reference's order, whatever the layout"""
+        if not odd:
+            return buf[r]                                        # a view: modified in place
+        return np.stack([np.roll(buf[r + CY[k], :, OPP[k]], -CX[k]) for k in range(9)], axis=1)
+
+    def store_canonical_row(r, vals):
+        if odd:
+            for k in range(9):
+                buf[r + CY[k], :, OPP[k]] = np.roll(vals[:, k], CX[k])
+
+    for t in range(iters):
+        if accel_row > 0:
+            vals = np.ascontiguousarray(canonical_row(accel_row))
+            oracle.accelerate_row(vals, ob[accel_row], density, accel)
+            if odd:
+                store_canonical_row(accel_row, vals)
+            else:
+                buf[accel_row] = vals
+        if not odd:
+            av[t] = oracle.slab_timestep(np.nan_to_num(buf, nan=0.0), tmp, ob, 1, rows + 1, omega) * inv
+            new = np.full_like(buf, np.nan)
+            for i in range(9):
+                new[1 - CY[i]:rows + 1 - CY[i], :, i] = np.roll(tmp[1:rows + 1, :, OPP[i]], -CX[i], axis=1)
+            # rows 0 and rows+1 of `new` belong to the neighbours' owned edge rows
+            from_south, from_north = swap_rows(new[rows + 1][:, SOUTH_PLANES], new[0][:, NORTH_PLANES], rank, size)
+            new[1][:, SOUTH_PLANES] = from_south             # written by the southern slab's last row
+            new[rows][:, NORTH_PLANES] = from_north          # written by the northern slab's first row
+            new[0] = np.nan
+            new[rows + 1] = np.nan
+            buf = new
+        else:
+            pulled = buf[1:rows + 1][:, :, OPP]                  # population j sits in slot opp(j) of its own cell
+            g = np.zeros_like(buf)
+            for j in range(9):                                   # lay them out so that the oracle's pull finds them
+                g[1 - CY[j]:rows + 1 - CY[j], :, j] = np.roll(pulled[:, :, j], -CX[j], axis=1)
+            av[t] = oracle.slab_timestep(g, tmp, ob, 1, rows + 1, omega) * inv
+            buf = np.full_like(buf, np.nan)
+            buf[1:rows + 1] = tmp[1:rows + 1]
+            exchange_halos(buf, rank, size)
+        odd ^= 1
+    if odd:
+        # canonical population k of an edge-row cell may live in the neighbour's owned edge row
+        from_south, from_north = swap_rows(buf[rows][:, NORTH_PLANES], buf[1][:, SOUTH_PLANES], rank, size)
+        ext = buf.copy()
+        ext[0][:, NORTH_PLANES] = from_south                 # the southern slab's last row, slots 2,5,6
+        ext[rows + 1][:, SOUTH_PLANES] = from_north          # the northern slab's first row, slots 4,7,8
+        out = np.empty((rows, nx, 9), np.float32)
+        for k in range(9):
+            out[:, :, k] = np.roll(ext[1 + CY[k]:rows + 1 + CY[k], :, OPP[k]], -CX[k], axis=1)
+        return out, av
+    return buf[1:rows + 1].copy(), av
+
+
+def worker(rank, size, port, args, out_queue, inplace=False):
     import os
     import sys
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -70,7 +161,7 @@ def worker(rank, size, port, args, out_queue):
     pkg = entry.load_package()
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
-        cells, av = run_slab(pkg, oracle_lib, rank, size, *args)
+        cells, av = (run_slab_inplace if inplace else run_slab)(pkg, oracle_lib, rank, size, *args)
         # the final reduction of the per-rank av_vels arrays (reference d2q9-bgk.c:396)
         total = torch.from_numpy(av.copy())
         dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)

@@ -18,10 +18,13 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("size,nx,ny", [(2, 32, 24), (2, 40, 17), (3, 16, 19)])
-def test_slab_ring_matches_single_domain(pkg, oracle, size, nx, ny):
+@pytest.mark.parametrize("size,nx,ny,inplace,iters", [(2, 32, 24, False, 25), (2, 40, 17, False, 25), (3, 16, 19, False, 25),
+                                                      (2, 32, 24, True, 12), (2, 40, 17, True, 13), (3, 16, 19, True, 9)])
+def test_slab_ring_matches_single_domain(pkg, oracle, size, nx, ny, inplace, iters):
+    """inplace: the one-buffer (AA access pattern) ring protocol -- what crosses the slabs in which step flavour --
+    ending in either layout."""
     rng = np.random.default_rng(size * 1000 + ny)
-    iters, density, accel, omega = 25, 0.1, 0.005, 1.85
+    density, accel, omega = 0.1, 0.005, 1.85
     obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))   # odd ny: open top/bottom, y-wrap in play
     cells0 = random_cells(rng, ny, nx, density)
     inv = pkg.free_cells_inv(obstacles)
@@ -33,7 +36,7 @@ def test_slab_ring_matches_single_domain(pkg, oracle, size, nx, ny):
     queue = ctx.Queue()
     port = free_port()
     args = (nx, ny, iters, density, accel, omega, obstacles, cells0)
-    procs = [ctx.Process(target=slab_ring.worker, args=(r, size, port, args, queue)) for r in range(size)]
+    procs = [ctx.Process(target=slab_ring.worker, args=(r, size, port, args, queue, inplace)) for r in range(size)]
     for p in procs:
         p.start()
     results = [queue.get(timeout=300) for _ in range(size)]
