@@ -114,6 +114,9 @@ struct lbm_b200 {
   // options
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
+  long opt_fused2 = 0, opt_band_rows = 64;
+  bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
+  int fused_grid = 0, fused_bands = 0, fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   int last_iters = 0;
   int graph_len = 0;
@@ -191,14 +194,38 @@ bool want_resident(const lbm_b200* h)
   return h->opt_resident == 1 || (cells >= kResidentAutoMinCells && cells <= kGraphAutoCells);
 }
 
+// Two timesteps per pass (kernel 5): single-slab ping-pong handles whose rows are at least two strips wide.
+bool want_fused2(const lbm_b200* h)
+{
+  return h->opt_fused2 == 1 && h->n_ranks == 1 && h->slabs.size() == 1 && !h->inplace && use_vec4(h) &&
+         h->nx >= 2 * lbm::kStripOut && h->ny >= 4;
+}
+
+constexpr int kFusedWarps = 8;
+constexpr size_t kFusedSmem = (size_t)kFusedWarps * 3 * 9 * 32 * sizeof(float4);
+
 void plan(lbm_b200* h)
 {
   h->resident = want_resident(h);
+  h->fused2 = want_fused2(h);
+  if (h->fused2) {
+    h->resident = false;
+    const Slab& s = h->slabs[0];
+    h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
+    h->fused_bands = (s.rows + (int)h->opt_band_rows - 1) / (int)h->opt_band_rows;
+    const long items = (long)h->fused_strips * h->fused_bands;
+    h->fused_grid = (int)std::min<long>((items + kFusedWarps - 1) / kFusedWarps, 1L << 30);
+    if (h->opt_ctas_per_sm > 0) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+      h->fused_grid = (int)std::min<long>(h->fused_grid, (long)sms * h->opt_ctas_per_sm);
+    }
+  }
   for (Slab& s : h->slabs) {
     if (h->n_ranks == 1) {
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
-      s.per_step = s.grid_full;
+      s.per_step = std::max(s.grid_full, h->fused2 ? h->fused_grid : 0);
     } else if (use_vec4(h)) {
       // one launch per step and slab: edge rows first, then the interior (csrc/lbm_kernels.cuh)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
@@ -490,6 +517,38 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
   return LBM_B200_OK;
 }
 
+// Two timesteps in one pass over HBM (kernel 5): partial slots `slot` and `slot`+1.
+int enqueue_fused2(lbm_b200* h, int slot, bool fold_last)
+{
+  Slab& s = h->slabs[0];
+  CUDA_TRY(cudaSetDevice(s.device));
+  StepArgs a = base_args(h, s, slot, false);
+  a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+  a.south_of_first = s.rows;
+  a.north_of_last = 1;
+  lbm::FusedArgs g{};
+  g.band_rows = (int)h->opt_band_rows;
+  g.bands = h->fused_bands;
+  g.strips = h->fused_strips;
+  g.accel_row = s.accel_row;
+  g.fold_last = fold_last ? 1 : 0;
+  g.partial_stride = s.per_step;
+  static bool attr_set[64] = {};
+  if (s.device < 64 && !attr_set[s.device]) {
+    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    attr_set[s.device] = true;
+  }
+  if (h->opt_cache_hint == 1) lbm::steps2_strip<1><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
+  else if (h->opt_cache_hint == 2) lbm::steps2_strip<2><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
+  else lbm::steps2_strip<0><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  h->cur ^= 1;
+  return LBM_B200_OK;
+}
+
 int enqueue_reduce(lbm_b200* h, int steps)
 {
   for (Slab& s : h->slabs) {
@@ -604,6 +663,8 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_MIN_CTAS")) h->opt_min_ctas = atol(e);
   if (const char* e = getenv("LBM_B200_CACHE_HINT")) h->opt_cache_hint = atol(e);
   if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
+  if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = atol(e) == 1;
+  if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(1L, atol(e));
 }
 
 }  // namespace
@@ -876,7 +937,7 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
     CUDA_TRY(cudaMemsetAsync(s.cursor, 0, sizeof(unsigned), s.stream));
   }
   int glen = (int)h->opt_graph_steps;
-  if (h->resident) glen = 0;
+  if (h->resident || h->fused2) glen = 0;
   if (glen < 0) {
     // auto: grids whose step kernel is launch-latency bound (a few microseconds) are replayed
     // from CUDA graphs -- measured 4.1 -> 2.7 us per step on the 128..256-wide decks
@@ -946,8 +1007,19 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
     }
     while (t < iters) {
       const int n = std::min(kChunkSteps, iters - t);
+      if (h->fused2) {
+        // fused passes and the single-step tail use different grids: slots are summed over per_step entries
+        Slab& s = h->slabs[0];
+        CUDA_TRY(cudaMemsetAsync(s.partials, 0, (size_t)n * s.per_step * sizeof(double), s.stream));
+      }
       for (int i = 0; i < n; i++) {
-        int rc = enqueue_step(h, i, t + i != iters - 1);
+        int rc;
+        if (h->fused2 && i + 1 < n) {                  // steps t+i and t+i+1 in one pass over HBM
+          rc = enqueue_fused2(h, i, t + i + 1 != iters - 1);
+          i++;
+        } else {
+          rc = enqueue_step(h, i, t + i != iters - 1);
+        }
         if (rc) return rc;
       }
       int rc = enqueue_reduce(h, n);
@@ -1130,6 +1202,12 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "resident")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "resident must be -1, 0 or 1");
     h->opt_resident = value;
+  } else if (!strcmp(key, "fused2")) {
+    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "fused2 must be 0 or 1");
+    h->opt_fused2 = value;
+  } else if (!strcmp(key, "band_rows")) {
+    if (value < 1 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 1..2^20");
+    h->opt_band_rows = value;
   } else if (!strcmp(key, "staging_bytes")) {
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
     h->opt_staging_bytes = value;
@@ -1153,7 +1231,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
 {
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
-  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1));
+  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->fused2 ? 5 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1)));
+  else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
+  else if (!strcmp(key, "band_rows")) *value = h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;

@@ -633,6 +633,178 @@ __device__ __forceinline__ float* locate(const Layout& l, float* buf, int k, int
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel 5 ("fused2"): TWO timesteps per pass over HBM.  The streaming kernels above move 72 B per cell and step
+// and sit at the HBM roofline; the only way past it is to touch DRAM less often.  Here a warp walks down a strip
+// of 120 owned columns: the first step is computed for the 128 aligned columns around the strip (4 redundant on
+// each side, so the second step finds its x-neighbours) and kept in a three-row ring in shared memory; the second
+// step pulls from that ring and stores to the other buffer.  Per cell and PAIR of steps: 36 B read + 36 B written
+// (+6.7 % redundant columns, +2/band_rows redundant rows) -- about half the DRAM traffic per step, at the price of
+// 1.07x the arithmetic; the kernel is bound by instruction issue, not by HBM.
+//   work item  = (band of `band_rows` rows, strip); one warp per item, no inter-warp synchronisation
+//   step 1     row y needs planes 2,5,6 of row y-1, 0,1,3 of row y and 4,7,8 of row y+1: every (row, plane) is
+//              loaded exactly once per strip, as in step_vec4 (128-bit loads + shuffles + end-lane scalars)
+//   step 2     row y needs step-1 rows y-1, y, y+1: 128-bit shared-memory loads + shuffles; lanes 1..30 own output
+// The arithmetic per cell and step is the same collide()/accelerate(): results are bit-identical to two launches
+// of step_vec4.  Single-slab handles only (a ring would need two halo rows).
+// ---------------------------------------------------------------------------------------
+constexpr int kStripOut = 120;    // owned columns per strip (30 lanes x 4)
+
+struct FusedArgs {
+  int band_rows;        // rows per work item
+  int bands, strips;
+  int accel_row;        // padded row of global row ny-2 (the first step always gets the second step's force folded in)
+  int fold_last;        // whether the second step folds the following step's force in
+  int partial_stride;   // doubles between the two steps' partials
+};
+
+template <int HINT>
+__global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const FusedArgs g)
+{
+  extern __shared__ float4 ring_all[];                       // [warps][3 rows][9 planes][32 lanes]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  float4* const ring = ring_all + (size_t)warp * (3 * 9 * 32);
+  const float* __restrict__ src = a.src;
+  float* __restrict__ dst = a.dst;
+  const size_t P = a.plane;
+  const int rows = a.row_last;                               // owned padded rows are 1..rows, periodic in y
+  const int nx = a.nx;
+  double acc1 = 0.0, acc2 = 0.0;
+
+  const long nitems = (long)g.bands * g.strips;
+  for (long item = (long)blockIdx.x * warps + warp; item < nitems; item += (long)gridDim.x * warps) {
+    const int band = (int)(item / g.strips);
+    const int strip = (int)(item - (long)band * g.strips);
+    const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
+    const int ye = min(yb + g.band_rows, rows);
+    // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
+    int gx = strip * kStripOut - 4 + 4 * lane;
+    if (gx < 0) gx += nx;
+    while (gx >= nx) gx -= nx;
+    const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
+    const int xw = (gx == 0) ? nx - 1 : gx - 1;
+    const int xe = (gx + 4 >= nx) ? 0 : gx + 4;
+
+    // ---- first step of row y (0-based, may be -1 or `rows`: periodic), into ring slot `slot` ----
+    auto step1 = [&](const int y, const int slot) {
+      const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
+      const int rs = (row == 1) ? rows : row - 1;
+      const int rn = (row == rows) ? 1 : row + 1;
+      const size_t o_c = (size_t)row * nx, o_s = (size_t)rs * nx, o_n = (size_t)rn * nx;
+      float4 c[9];
+      c[0] = load4<HINT>(src + 0 * P + o_c + gx);
+      c[1] = load4<HINT>(src + 1 * P + o_c + gx);
+      c[2] = load4<HINT>(src + 2 * P + o_s + gx);
+      c[3] = load4<HINT>(src + 3 * P + o_c + gx);
+      c[4] = load4<HINT>(src + 4 * P + o_n + gx);
+      c[5] = load4<HINT>(src + 5 * P + o_s + gx);
+      c[6] = load4<HINT>(src + 6 * P + o_s + gx);
+      c[7] = load4<HINT>(src + 7 * P + o_n + gx);
+      c[8] = load4<HINT>(src + 8 * P + o_n + gx);
+      const uint32_t mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (gx >> 5));
+      float e_c = 0.f, e_s = 0.f, e_n = 0.f;
+      if (lane == 0 || lane == 31) {
+        const bool w = (lane == 0);
+        e_c = load1<HINT>(w ? src + 1 * P + o_c + xw : src + 3 * P + o_c + xe);
+        e_s = load1<HINT>(w ? src + 5 * P + o_s + xw : src + 6 * P + o_s + xe);
+        e_n = load1<HINT>(w ? src + 8 * P + o_n + xw : src + 7 * P + o_n + xe);
+      }
+      const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+      const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+      const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+      const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+      const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+      const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+      const bool we = (lane == 0), ee = (lane == 31);
+      float f[4][9];
+      f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+      f[0][1] = we ? e_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+      f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+      f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = ee ? e_c : dn3;
+      f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+      f[0][5] = we ? e_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+      f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = ee ? e_s : dn6;
+      f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = ee ? e_n : dn7;
+      f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+      const unsigned bits = (mw >> (gx & 31)) & 0xFu;
+      const bool fold = (row == g.accel_row);
+      float u4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool blocked = (bits >> j) & 1u;
+        const float u = collide(f[j], blocked, a.c.omega);
+        u4 = (j == 0) ? u : add(u4, u);
+        if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+      }
+      if (owned && y >= yb && y < ye) acc1 += (double)u4;
+      __syncwarp();                                          // the slot's previous readers are done
+      float4* out = ring + slot * (9 * 32) + lane;
+#pragma unroll
+      for (int k = 0; k < 9; k++) out[k * 32] = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+    };
+
+    // ---- second step of row y (0-based, owned) from ring slots s_s (row y-1), s_c (row y), s_n (row y+1) ----
+    auto step2 = [&](const int y, const int s_s, const int s_c, const int s_n) {
+      const int row = y + 1;
+      __syncwarp();                                          // the three rows are complete
+      const float4* rs_ = ring + s_s * (9 * 32) + lane;
+      const float4* rc_ = ring + s_c * (9 * 32) + lane;
+      const float4* rn_ = ring + s_n * (9 * 32) + lane;
+      float4 c[9];
+      c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[3 * 32];
+      c[2] = rs_[2 * 32]; c[5] = rs_[5 * 32]; c[6] = rs_[6 * 32];
+      c[4] = rn_[4 * 32]; c[7] = rn_[7 * 32]; c[8] = rn_[8 * 32];
+      const uint32_t mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (gx >> 5));
+      const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+      const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+      const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+      const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+      const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+      const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+      if (!owned) return;
+      float f[4][9];
+      f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+      f[0][1] = up1;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+      f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+      f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = dn3;
+      f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+      f[0][5] = up5;    f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+      f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
+      f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
+      f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+      const unsigned bits = (mw >> (gx & 31)) & 0xFu;
+      const bool fold = g.fold_last && (row == g.accel_row);
+      float u4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool blocked = (bits >> j) & 1u;
+        const float u = collide(f[j], blocked, a.c.omega);
+        u4 = (j == 0) ? u : add(u4, u);
+        if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+      }
+      acc2 += (double)u4;
+      const size_t o = (size_t)row * nx + gx;
+#pragma unroll
+      for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+    };
+
+    // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
+    step1(yb - 1, 0);
+    step1(yb, 1);
+    int s_s = 0, s_c = 1, s_n = 2;
+    for (int y = yb; y < ye; y++) {
+      step1(y + 1, s_n);
+      step2(y, s_s, s_c, s_n);
+      const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+    }
+    __syncwarp();
+  }
+
+  block_sum_to(acc1, a.partials + blockIdx.x);
+  __syncthreads();
+  block_sum_to(acc2, a.partials + g.partial_stride + blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------
 // Kernel 3 ("resident"): many timesteps in ONE cooperative launch for grids that are launch-latency
 // bound (the shipped 128..1024-wide decks: a step is a few microseconds of work).  The same pass as
 // step_vec4 runs `steps` times with a grid-wide barrier in between and the two buffers swapping roles;

@@ -372,3 +372,51 @@ def test_switching_kernels_on_a_ring_keeps_the_handshake_consistent(pkg, oracle)
         av.append(sim.run(6))
         assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
         assert_av(np.concatenate(av), ref_av, ref_exact)
+
+
+# ---- two timesteps per pass over HBM (kernel 5, "fused2") -----------------------------------------------------------
+
+@pytest.mark.parametrize("nx,ny,band", [(256, 24, 64), (360, 19, 5), (244, 33, 7), (1024, 16, 4), (240, 9, 3), (2048, 40, 64)])
+@pytest.mark.parametrize("iters", [2, 5, 16])
+def test_fused2_bit_exact(pkg, oracle, nx, ny, band, iters):
+    """Pairs of timesteps fused into one pass (first step into a shared-memory ring, second step out of it): ragged last
+    strips (nx not a multiple of 120), ragged last bands, bands of 3..64 rows, odd step counts (a single-step tail),
+    x- and y-wrap, blocked cells and non-forced cells in the accelerated row."""
+    rng = np.random.default_rng(nx + 31 * ny + iters)
+    obstacles = random_obstacles(rng, ny, nx, 0.10, walls=(ny % 2 == 0))
+    obstacles[:, 0] = rng.random(ny) < 0.5
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    obstacles[ny - 2, :] = rng.random(nx) < 0.2
+    cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, : nx // 3, 3] = 1e-5
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("band_rows", band)
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
+        sim.set_cells(cells0)
+        assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+        assert sim.get_option("launches") <= iters // 2 + iters % 2 + 4
+
+
+def test_fused2_runs_compose_and_match_the_single_step_kernel(pkg, oracle):
+    rng = np.random.default_rng(91)
+    nx, ny = 600, 70
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, 13)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("fused2", 1)
+        sim.set_option("band_rows", 16)
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(3), sim.run(4), sim.run(0), sim.run(1), sim.run(5)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref_cells))
+        assert_av(av, ref_av, ref_exact)
+        sim.set_option("fused2", 0)                          # and back to one step per launch on the same handle
+        assert sim.get_option("kernel") in (2, 3)
+
+
+def test_fused2_is_refused_where_it_does_not_apply(pkg):
+    ob = np.zeros((12, 128), np.int32)
+    with pkg.Simulation(128, 12, DENSITY, ACCEL, OMEGA, ob) as sim:     # narrower than two strips: stays on kernel 2
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") != 5 and sim.get_option("fused2") == 0
