@@ -202,7 +202,7 @@ bool want_fused2(const lbm_b200* h)
 }
 
 constexpr int kFusedWarps = 8;
-constexpr size_t kFusedSmem = (size_t)kFusedWarps * 3 * 9 * 32 * sizeof(float4);
+constexpr size_t kFusedSmem = (size_t)kFusedWarps * lbm::kFusedWarpFloat4 * sizeof(float4);
 
 void plan(lbm_b200* h)
 {

@@ -657,12 +657,33 @@ struct FusedArgs {
   int partial_stride;   // doubles between the two steps' partials
 };
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// shared memory of one warp: a three-row ring of the six first-step planes the second step reads later (planes
+// 4,7,8 of a row are consumed straight from registers), one staging row filled by cp.async one row ahead of the
+// arithmetic, and the six end-lane scalars of that row
+constexpr int kRingPlanes = 6;                                   // ring order: planes 0, 1, 3, 2, 5, 6
+constexpr int kFusedWarpFloat4 = 3 * kRingPlanes * 32 + 9 * 32 + 2;   // + 2 float4 for the end-lane scalars
+
 template <int HINT>
 __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const FusedArgs g)
 {
-  extern __shared__ float4 ring_all[];                       // [warps][3 rows][9 planes][32 lanes]
+  extern __shared__ float4 fused_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  float4* const ring = ring_all + (size_t)warp * (3 * 9 * 32);
+  float4* const ring = fused_smem + (size_t)warp * kFusedWarpFloat4;   // [3][6][32]
+  float4* const stage = ring + 3 * kRingPlanes * 32;                   // [9][32]
+  float* const ends = reinterpret_cast<float*>(stage + 9 * 32);        // [0..2] west (lane 0), [3..5] east (lane 31)
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
@@ -683,38 +704,58 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
     const int xw = (gx == 0) ? nx - 1 : gx - 1;
     const int xe = (gx + 4 >= nx) ? 0 : gx + 4;
+    const uint32_t* const mask_x = a.mask + (gx >> 5);
+    const int mask_shift = gx & 31;
 
-    // ---- first step of row y (0-based, may be -1 or `rows`: periodic), into ring slot `slot` ----
-    auto step1 = [&](const int y, const int slot) {
+    // ---- asynchronous copy of what the first step of row y (0-based; -1 and `rows` wrap) pulls, into the
+    //      staging row; returns the row's obstacle bits of this lane's four columns ----
+    auto issue = [&](const int y) -> unsigned {
       const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
       const int rs = (row == 1) ? rows : row - 1;
       const int rn = (row == rows) ? 1 : row + 1;
-      const size_t o_c = (size_t)row * nx, o_s = (size_t)rs * nx, o_n = (size_t)rn * nx;
-      float4 c[9];
-      c[0] = load4<HINT>(src + 0 * P + o_c + gx);
-      c[1] = load4<HINT>(src + 1 * P + o_c + gx);
-      c[2] = load4<HINT>(src + 2 * P + o_s + gx);
-      c[3] = load4<HINT>(src + 3 * P + o_c + gx);
-      c[4] = load4<HINT>(src + 4 * P + o_n + gx);
-      c[5] = load4<HINT>(src + 5 * P + o_s + gx);
-      c[6] = load4<HINT>(src + 6 * P + o_s + gx);
-      c[7] = load4<HINT>(src + 7 * P + o_n + gx);
-      c[8] = load4<HINT>(src + 8 * P + o_n + gx);
-      const uint32_t mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (gx >> 5));
-      float e_c = 0.f, e_s = 0.f, e_n = 0.f;
-      if (lane == 0 || lane == 31) {
-        const bool w = (lane == 0);
-        e_c = load1<HINT>(w ? src + 1 * P + o_c + xw : src + 3 * P + o_c + xe);
-        e_s = load1<HINT>(w ? src + 5 * P + o_s + xw : src + 6 * P + o_s + xe);
-        e_n = load1<HINT>(w ? src + 8 * P + o_n + xw : src + 7 * P + o_n + xe);
+      const float* pc = src + (size_t)row * nx;
+      const float* ps = src + (size_t)rs * nx;
+      const float* pn = src + (size_t)rn * nx;
+      cp_async16(stage + 0 * 32 + lane, pc + 0 * P + gx);
+      cp_async16(stage + 1 * 32 + lane, pc + 1 * P + gx);
+      cp_async16(stage + 2 * 32 + lane, ps + 2 * P + gx);
+      cp_async16(stage + 3 * 32 + lane, pc + 3 * P + gx);
+      cp_async16(stage + 4 * 32 + lane, pn + 4 * P + gx);
+      cp_async16(stage + 5 * 32 + lane, ps + 5 * P + gx);
+      cp_async16(stage + 6 * 32 + lane, ps + 6 * P + gx);
+      cp_async16(stage + 7 * 32 + lane, pn + 7 * P + gx);
+      cp_async16(stage + 8 * 32 + lane, pn + 8 * P + gx);
+      if (lane == 0) {
+        cp_async4(ends + 0, pc + 1 * P + xw);
+        cp_async4(ends + 1, ps + 5 * P + xw);
+        cp_async4(ends + 2, pn + 8 * P + xw);
+      } else if (lane == 31) {
+        cp_async4(ends + 3, pc + 3 * P + xe);
+        cp_async4(ends + 4, ps + 6 * P + xe);
+        cp_async4(ends + 5, pn + 7 * P + xe);
       }
+      cp_async_commit();
+      return (__ldg(mask_x + (size_t)(row - 1) * a.mask_row_words) >> mask_shift) & 0xFu;
+    };
+
+    // ---- first step of row y out of the staging row (bits = its obstacle bits); the six planes the second step
+    //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
+    //      row y+1 is issued as soon as the staging row has been read; its obstacle bits are returned. ----
+    auto step1 = [&](const int y, const unsigned bits, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
+      const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
+      cp_async_wait_all();
+      float4 c[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) c[k] = stage[k * 32 + lane];
+      const bool we = (lane == 0), ee = (lane == 31);
+      float e_c = 0.f, e_s = 0.f, e_n = 0.f;
+      if (we || ee) { e_c = ends[we ? 0 : 3]; e_s = ends[we ? 1 : 4]; e_n = ends[we ? 2 : 5]; }
       const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
       const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
       const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
       const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
       const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
       const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-      const bool we = (lane == 0), ee = (lane == 31);
       float f[4][9];
       f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
       f[0][1] = we ? e_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
@@ -725,7 +766,9 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = ee ? e_s : dn6;
       f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = ee ? e_n : dn7;
       f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-      const unsigned bits = (mw >> (gx & 31)) & 0xFu;
+      // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
+      // flies during both steps' arithmetic
+      const unsigned bits_next = ahead ? issue(y + 1) : 0u;
       const bool fold = (row == g.accel_row);
       float u4 = 0.f;
 #pragma unroll
@@ -737,23 +780,30 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       }
       if (owned && y >= yb && y < ye) acc1 += (double)u4;
       __syncwarp();                                          // the slot's previous readers are done
-      float4* out = ring + slot * (9 * 32) + lane;
-#pragma unroll
-      for (int k = 0; k < 9; k++) out[k * 32] = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+      float4* out = ring + slot * (kRingPlanes * 32) + lane;
+      out[0 * 32] = make_float4(f[0][0], f[1][0], f[2][0], f[3][0]);
+      out[1 * 32] = make_float4(f[0][1], f[1][1], f[2][1], f[3][1]);
+      out[2 * 32] = make_float4(f[0][3], f[1][3], f[2][3], f[3][3]);
+      out[3 * 32] = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
+      out[4 * 32] = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
+      out[5 * 32] = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
+      k4 = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
+      k7 = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
+      k8 = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
+      return bits_next;
     };
 
-    // ---- second step of row y (0-based, owned) from ring slots s_s (row y-1), s_c (row y), s_n (row y+1) ----
-    auto step2 = [&](const int y, const int s_s, const int s_c, const int s_n) {
+    // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
+    //      row y (slot s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran ----
+    auto step2 = [&](const int y, const unsigned bits, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
       const int row = y + 1;
-      __syncwarp();                                          // the three rows are complete
-      const float4* rs_ = ring + s_s * (9 * 32) + lane;
-      const float4* rc_ = ring + s_c * (9 * 32) + lane;
-      const float4* rn_ = ring + s_n * (9 * 32) + lane;
+      __syncwarp();                                          // ring rows are complete
+      const float4* rs_ = ring + s_s * (kRingPlanes * 32) + lane;
+      const float4* rc_ = ring + s_c * (kRingPlanes * 32) + lane;
       float4 c[9];
-      c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[3 * 32];
-      c[2] = rs_[2 * 32]; c[5] = rs_[5 * 32]; c[6] = rs_[6 * 32];
-      c[4] = rn_[4 * 32]; c[7] = rn_[7 * 32]; c[8] = rn_[8 * 32];
-      const uint32_t mw = __ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (gx >> 5));
+      c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[2 * 32];
+      c[2] = rs_[3 * 32]; c[5] = rs_[4 * 32]; c[6] = rs_[5 * 32];
+      c[4] = k4; c[7] = k7; c[8] = k8;
       const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
       const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
       const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
@@ -771,7 +821,6 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
       f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
       f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-      const unsigned bits = (mw >> (gx & 31)) & 0xFu;
       const bool fold = g.fold_last && (row == g.accel_row);
       float u4 = 0.f;
 #pragma unroll
@@ -788,12 +837,15 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     };
 
     // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
-    step1(yb - 1, 0);
-    step1(yb, 1);
+    float4 k4, k7, k8;
+    unsigned bits_s = issue(yb - 1);
+    unsigned bits_c = step1(yb - 1, bits_s, 0, true, k4, k7, k8);          // -> bits of row yb
+    unsigned bits_n = step1(yb, bits_c, 1, true, k4, k7, k8);              // -> bits of row yb+1
     int s_s = 0, s_c = 1, s_n = 2;
     for (int y = yb; y < ye; y++) {
-      step1(y + 1, s_n);
-      step2(y, s_s, s_c, s_n);
+      const unsigned bits_nn = step1(y + 1, bits_n, s_n, y + 1 < ye, k4, k7, k8);
+      step2(y, bits_c, s_s, s_c, k4, k7, k8);
+      bits_c = bits_n; bits_n = bits_nn;
       const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
     }
     __syncwarp();
