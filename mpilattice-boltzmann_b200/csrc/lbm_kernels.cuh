@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     const int mask_shift = gx & 31;
 
     // ---- asynchronous copy of what the first step of row y (0-based; -1 and `rows` wrap) pulls, into the
-    //      staging row; returns the row's obstacle bits of this lane's four columns ----
+    //      staging row; returns the row's obstacle word of this lane's columns (its bits are >> mask_shift) ----
     auto issue = [&](const int y) -> unsigned {
       const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
       const int rs = (row == 1) ? rows : row - 1;
@@ -735,13 +735,13 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         cp_async4(ends + 5, pn + 7 * P + xe);
       }
       cp_async_commit();
-      return (__ldg(mask_x + (size_t)(row - 1) * a.mask_row_words) >> mask_shift) & 0xFu;
+      return __ldg(mask_x + (size_t)(row - 1) * a.mask_row_words);     // used a whole row later: no stall here
     };
 
     // ---- first step of row y out of the staging row (bits = its obstacle bits); the six planes the second step
     //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
     //      row y+1 is issued as soon as the staging row has been read; its obstacle bits are returned. ----
-    auto step1 = [&](const int y, const unsigned bits, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
+    auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
       const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
       cp_async_wait_all();
       float4 c[9];
@@ -769,6 +769,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
       // flies during both steps' arithmetic
       const unsigned bits_next = ahead ? issue(y + 1) : 0u;
+      const unsigned bits = mword >> mask_shift;
       const bool fold = (row == g.accel_row);
       float u4 = 0.f;
 #pragma unroll
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
     // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
     //      row y (slot s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran ----
-    auto step2 = [&](const int y, const unsigned bits, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
+    auto step2 = [&](const int y, const unsigned mword, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
       const int row = y + 1;
       __syncwarp();                                          // ring rows are complete
       const float4* rs_ = ring + s_s * (kRingPlanes * 32) + lane;
@@ -821,6 +822,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
       f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
       f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+      const unsigned bits = mword >> mask_shift;
       const bool fold = g.fold_last && (row == g.accel_row);
       float u4 = 0.f;
 #pragma unroll
