@@ -54,6 +54,26 @@ def test_full_size_inplace(pkg, oracle):
             assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
 
 
+def test_full_size_fused2(pkg, oracle):
+    """Two timesteps per pass at 16384 x 16384 (137 strips of 120 columns -- the last one 64 wide --, 256 bands of 64
+    rows): 7 steps = three fused passes and a single-step tail, against the tiled 128-wide oracle."""
+    period, iters = 128, 7
+    rng = np.random.default_rng(44)
+    narrow = narrow_pattern(period, rng)
+    cells = oracle.init_cells(period, NY, DENSITY)
+    _, av_ref = oracle.run(cells, narrow, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(narrow), exact=True)
+    ref_fields = oracle.final_state(cells, narrow, DENSITY)
+    obstacles = np.tile(narrow, (1, NX // period))
+    with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
+        av = sim.run(iters)
+        assert sim.get_option("launches") < 12
+        for got, want in zip(sim.final_state(), ref_fields):
+            assert np.array_equal(bits(got), bits(np.tile(want, (1, NX // period))))
+        assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
+
+
 def narrow_pattern(period, rng):
     ob = (rng.random((NY, period)) < 0.02).astype(np.int32)
     ob[0, :] = ob[-1, :] = 1                     # the synthetic deck's channel walls (SURVEY 8d)

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--hints", default="0,1,2")
     ap.add_argument("--graph-steps", default="0")
     ap.add_argument("--resident", default="0")
+    ap.add_argument("--fused2", action="store_true", help="two timesteps per pass over HBM (kernel 5)")
+    ap.add_argument("--band-rows", default="64")
     ap.add_argument("--inplace", action="store_true", help="one population buffer (AA access pattern); kernels/min-ctas/resident are ignored")
     args = ap.parse_args()
     pkg = entry.load_package()
@@ -39,13 +41,17 @@ def main():
         args.kernels, args.min_ctas, args.resident = "4", "2", "0"
     with pkg.Simulation(args.nx, args.ny, 0.1, 0.005, 1.85, obstacles, inplace=args.inplace) as sim:
         lists = [[int(v) for v in s.split(",")] for s in (args.kernels, args.min_ctas, args.ctas_per_sm, args.hints, args.graph_steps, args.resident)]
-        for kernel, min_ctas, per_sm, hint, graph, resident in itertools.product(*lists):
+        bands = [int(v) for v in args.band_rows.split(",")] if args.fused2 else [0]
+        for (kernel, min_ctas, per_sm, hint, graph, resident), band in itertools.product(itertools.product(*lists), bands):
             if kernel == 1 and (min_ctas != lists[1][0] or hint != lists[3][0]):
                 continue
             if not args.inplace:
                 sim.set_option("resident", resident)
                 sim.set_option("kernel", kernel)
                 sim.set_option("min_ctas", min_ctas)
+            if args.fused2:
+                sim.set_option("band_rows", band)
+                sim.set_option("fused2", 1)
             sim.set_option("ctas_per_sm", per_sm)
             sim.set_option("cache_hint", hint)
             sim.set_option("graph_steps", graph)
@@ -56,7 +62,7 @@ def main():
                 ms = sim.elapsed_ms()
                 best = ms if best is None else min(best, ms)
             mlups = args.nx * args.ny * args.timesteps / (best * 1e-3) / 1e6
-            rec = {"kernel": kernel, "min_ctas": min_ctas, "ctas_per_sm": per_sm, "cache_hint": hint, "graph_steps": graph, "resident": resident,
+            rec = {"band_rows": band, "kernel": sim.get_option("kernel"), "min_ctas": min_ctas, "ctas_per_sm": per_sm, "cache_hint": hint, "graph_steps": graph, "resident": resident,
                    "grid": sim.get_option("grid"), "threads": sim.get_option("threads"),
                    "us_per_step": round(best * 1e3 / args.timesteps, 2), "mlups": round(mlups, 1),
                    "gbs": round(mlups * 72e-3, 1)}
