@@ -47,6 +47,7 @@ enum FlagWord { kFromSouth = 0, kFromNorth = 1, kEpoch = 2, kDone = 3, kFlagWord
 
 struct Neighbour {
   float* buf[2] = {nullptr, nullptr};   // the neighbour's two population buffers (peer or IPC mapped)
+  uint32_t* mask = nullptr;             // the neighbour's obstacle words (only mapped while connecting)
   unsigned* flags = nullptr;            // the neighbour's flag words
   size_t plane = 0;
   int rows = 0;
@@ -77,12 +78,14 @@ struct Slab {
   int threads_edge = 256, grid_edge = 0;
   int threads_int = 256, grid_int = 0;
   int per_step = 1;
+  int fused_grid = 0, fused_bands = 0, fused_band_rows = 0;   // two-steps-per-pass kernel (kernel 5)
   std::vector<cudaGraphExec_t> graphs;  // [parity]
 };
 
 struct IpcBlob {
   cudaIpcMemHandle_t buf[2];
   cudaIpcMemHandle_t flags;
+  cudaIpcMemHandle_t mask;
   unsigned long long plane;
   int rows;
   int device;
@@ -116,7 +119,7 @@ struct lbm_b200 {
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = 0, opt_band_rows = 64;
   bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
-  int fused_grid = 0, fused_bands = 0, fused_strips = 0;
+  int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   int last_iters = 0;
   int graph_len = 0;
@@ -194,11 +197,11 @@ bool want_resident(const lbm_b200* h)
   return h->opt_resident == 1 || (cells >= kResidentAutoMinCells && cells <= kGraphAutoCells);
 }
 
-// Two timesteps per pass (kernel 5): single-slab ping-pong handles whose rows are at least two strips wide.
+// Two timesteps per pass (kernel 5): ping-pong handles whose rows are at least two strips wide; on a ring every
+// slab needs four rows (the driven row ny-2 must not be a row a neighbour recomputes).
 bool want_fused2(const lbm_b200* h)
 {
-  return h->opt_fused2 == 1 && h->n_ranks == 1 && h->slabs.size() == 1 && !h->inplace && use_vec4(h) &&
-         h->nx >= 2 * lbm::kStripOut && h->ny >= 4;
+  return h->opt_fused2 == 1 && !h->inplace && use_vec4(h) && h->nx >= 2 * lbm::kStripOut && h->ny / h->n_ranks >= 4;
 }
 
 constexpr int kFusedWarps = 8;
@@ -210,27 +213,37 @@ void plan(lbm_b200* h)
   h->fused2 = want_fused2(h);
   if (h->fused2) {
     h->resident = false;
-    const Slab& s = h->slabs[0];
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
-    h->fused_bands = (s.rows + (int)h->opt_band_rows - 1) / (int)h->opt_band_rows;
-    const long items = (long)h->fused_strips * h->fused_bands;
-    h->fused_grid = (int)std::min<long>((items + kFusedWarps - 1) / kFusedWarps, 1L << 30);
-    if (h->opt_ctas_per_sm > 0) {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
-      h->fused_grid = (int)std::min<long>(h->fused_grid, (long)sms * h->opt_ctas_per_sm);
+    for (Slab& s : h->slabs) {
+      // bands of ~band_rows rows, balanced; the first and the last band hold at least two rows (a ring slab pushes
+      // two rows per direction and publishes them from one work item)
+      int bands = std::max(1, (s.rows + (int)h->opt_band_rows - 1) / (int)h->opt_band_rows);
+      int per = (s.rows + bands - 1) / bands;
+      while (bands > 1 && (per < 2 || s.rows - (bands - 1) * per < 2)) {
+        bands--;
+        per = (s.rows + bands - 1) / bands;
+      }
+      s.fused_bands = bands;
+      s.fused_band_rows = per;
+      const long items = (long)h->fused_strips * bands;
+      s.fused_grid = (int)std::min<long>((items + kFusedWarps - 1) / kFusedWarps, 1L << 30);
+      if (h->opt_ctas_per_sm > 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+        s.fused_grid = (int)std::min<long>(s.fused_grid, (long)sms * h->opt_ctas_per_sm);
+      }
     }
   }
   for (Slab& s : h->slabs) {
     if (h->n_ranks == 1) {
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
-      s.per_step = std::max(s.grid_full, h->fused2 ? h->fused_grid : 0);
+      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_grid : 0);
     } else if (use_vec4(h)) {
       // one launch per step and slab: edge rows first, then the interior (csrc/lbm_kernels.cuh)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
       s.grid_edge = s.grid_int = 0;
-      s.per_step = s.grid_full;
+      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_grid : 0);
     } else {
       plan_region(h, s.device, 2, &s.threads_edge, &s.grid_edge);
       plan_region(h, s.device, s.rows - 2, &s.threads_int, &s.grid_int);
@@ -257,12 +270,23 @@ double now_s()
   return ts.tv_sec + ts.tv_nsec * 1e-9;
 }
 
+// kFlagWords for the slab-level handshake, then per direction one word per 128-cell chunk (kernels 2 and 4) or per
+// 120-column strip (kernel 5), whichever is more
+size_t flag_word_count(int nx)
+{
+  const size_t chunks = (size_t)((nx + lbm::kSegCells - 1) / lbm::kSegCells);
+  const size_t strips = (size_t)((nx + lbm::kStripOut - 1) / lbm::kStripOut);
+  return kFlagWords + 2 * std::max(chunks, strips);
+}
+
 int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
 {
   const bool trace = getenv("LBM_B200_TRACE") != nullptr;
   const double t0 = now_s();
   CUDA_TRY(cudaSetDevice(s.device));
-  s.plane = (size_t)(s.rows + 2) * h->nx;
+  // padded rows: 0 and rows+1 are the halo rows next to the slab, rows+2 / rows+3 the second halo rows (the
+  // southern / northern neighbour's row one further away; used by the two-steps-per-pass kernel on a ring)
+  s.plane = (size_t)(s.rows + 4) * h->nx;
   const size_t bytes = 9 * s.plane * sizeof(float);
   for (int b = 0; b < (h->inplace ? 1 : 2); b++) {
     cudaError_t e = cudaMalloc(&s.buf[b], bytes);
@@ -271,7 +295,7 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   }
   // flag words: kFlagWords for the slab-level handshake, then one per 128-cell chunk from the south and one per
   // chunk from the north (csrc/lbm_kernels.cuh, warp_peer_wait)
-  const size_t flag_words = kFlagWords + 2 * (size_t)((h->nx + lbm::kSegCells - 1) / lbm::kSegCells);
+  const size_t flag_words = flag_word_count(h->nx);
   CUDA_TRY(cudaMalloc(&s.flags, flag_words * sizeof(unsigned)));
   CUDA_TRY(cudaMemset(s.flags, 0, flag_words * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&s.cursor, sizeof(unsigned)));
@@ -282,9 +306,11 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   const double t1 = now_s();
   // obstacle rows: upload the reference's int-per-cell array into the (still unused) second population
   // buffer and bit-pack it on the device: 32 cells per word, rows padded to whole words
-  const size_t words = (size_t)s.rows * h->mask_row_words;
+  // (three more rows of words follow the slab's own: the neighbours' rows -1, `rows` and -2, see set_halo_mask)
+  const size_t words = (size_t)(s.rows + 3) * h->mask_row_words;
   const size_t cells = (size_t)s.rows * h->nx;
   CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(s.mask, 0, std::max<size_t>(words, 1) * sizeof(uint32_t), s.stream));
   int* staged = reinterpret_cast<int*>(s.buf[h->inplace ? 0 : 1]);   // 4 of the buffer's 36 bytes per cell
   CUDA_TRY(cudaMemcpyAsync(staged, obstacles_rows, cells * sizeof(int), cudaMemcpyHostToDevice, s.stream));
   {
@@ -310,6 +336,26 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
             t1 - t0, t2 - t1, now_s() - t2);
   const int accel_global = h->ny - 2;
   s.accel_row = (accel_global >= s.first_row && accel_global < s.first_row + s.rows) ? accel_global - s.first_row + 1 : -1;
+  return LBM_B200_OK;
+}
+
+// Obstacle words of the three neighbour rows a ring slab computes redundantly in the two-steps-per-pass kernel:
+// word row `rows` = the southern neighbour's last row (y = -1), rows+1 = the northern neighbour's first row
+// (y = rows), rows+2 = the southern neighbour's second-to-last row (y = -2, only for the body-force pre-pass).
+int set_halo_mask(lbm_b200* h, Slab& s, const int* row_m1, const int* row_p, const int* row_m2)
+{
+  CUDA_TRY(cudaSetDevice(s.device));
+  int* staged = nullptr;
+  CUDA_TRY(cudaMalloc(&staged, 3 * (size_t)h->nx * sizeof(int)));
+  const int* src[3] = {row_m1, row_p, row_m2};
+  for (int i = 0; i < 3; i++)
+    CUDA_TRY(cudaMemcpyAsync(staged + (size_t)i * h->nx, src[i], (size_t)h->nx * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  const long warps = 3L * ((h->mask_row_words + 31) / 32);
+  lbm::pack_mask<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s.stream>>>(staged, h->nx, 3, h->mask_row_words,
+                                                                           s.mask + (size_t)s.rows * h->mask_row_words, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  CUDA_TRY(cudaFree(staged));
   return LBM_B200_OK;
 }
 
@@ -517,34 +563,55 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
   return LBM_B200_OK;
 }
 
-// Two timesteps in one pass over HBM (kernel 5): partial slots `slot` and `slot`+1.
-int enqueue_fused2(lbm_b200* h, int slot, bool fold_last)
+// Two timesteps in one pass over HBM (kernel 5): partial slots `slot` and `slot`+1 -- or, with `single`, the odd
+// last step of a run on a ring through the same strips (so that the strip-level handshake stays the only protocol
+// in use and the neighbours' two halo rows are refreshed).
+int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
 {
-  Slab& s = h->slabs[0];
-  CUDA_TRY(cudaSetDevice(s.device));
-  StepArgs a = base_args(h, s, slot, false);
-  a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
-  a.south_of_first = s.rows;
-  a.north_of_last = 1;
-  lbm::FusedArgs g{};
-  g.band_rows = (int)h->opt_band_rows;
-  g.bands = h->fused_bands;
-  g.strips = h->fused_strips;
-  g.accel_row = s.accel_row;
-  g.fold_last = fold_last ? 1 : 0;
-  g.partial_stride = s.per_step;
   static bool attr_set[64] = {};
-  if (s.device < 64 && !attr_set[s.device]) {
-    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    attr_set[s.device] = true;
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    if (s.device < 64 && !attr_set[s.device]) {
+      const int bytes = (int)kFusedSmem;
+      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      attr_set[s.device] = true;
+    }
+    StepArgs a = base_args(h, s, slot, false);
+    a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+    a.south_of_first = s.rows;
+    a.north_of_last = 1;
+    lbm::FusedArgs g{};
+    g.band_rows = s.fused_band_rows;
+    g.bands = s.fused_bands;
+    g.strips = h->fused_strips;
+    g.accel_row = s.accel_row;
+    g.fold_last = fold_last ? 1 : 0;
+    g.partial_stride = s.per_step;
+    const dim3 grid(s.fused_grid), block(kFusedWarps * 32);
+    if (h->n_ranks == 1) {
+      if (h->opt_cache_hint == 1) lbm::steps2_strip<1, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      else if (h->opt_cache_hint == 2) lbm::steps2_strip<2, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      else lbm::steps2_strip<0, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+    } else {
+      peer_args(h, s, a);
+      const int strips = h->fused_strips;                    // one flag word per strip and direction
+      a.wait_from_south = s.flags + kFlagWords;
+      a.wait_from_north = s.flags + kFlagWords + strips;
+      a.signal_north = s.north.flags + kFlagWords;
+      a.signal_south = s.south.flags + kFlagWords + strips;
+      g.south_rows = s.south.rows;
+      g.north_rows = s.north.rows;
+      // (halo rows are written by the neighbours: L2-coherent loads, HINT 3 -- irrelevant for cp.async.cg)
+      if (single) lbm::steps2_strip<3, true, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      else lbm::steps2_strip<3, true, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
   }
-  if (h->opt_cache_hint == 1) lbm::steps2_strip<1><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
-  else if (h->opt_cache_hint == 2) lbm::steps2_strip<2><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
-  else lbm::steps2_strip<0><<<h->fused_grid, kFusedWarps * 32, kFusedSmem, s.stream>>>(a, g);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
   h->cur ^= 1;
   return LBM_B200_OK;
 }
@@ -616,7 +683,7 @@ int build_graphs(lbm_b200* h, int len)
 int resync_flags(lbm_b200* h)
 {
   if (h->n_ranks == 1) return LBM_B200_OK;
-  const size_t words = kFlagWords + 2 * (size_t)((h->nx + lbm::kSegCells - 1) / lbm::kSegCells);
+  const size_t words = flag_word_count(h->nx);
   std::vector<unsigned> host(words);
   for (Slab& s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
@@ -626,6 +693,30 @@ int resync_flags(lbm_b200* h)
     host[kDone] = 0;
     for (int i = kDone + 1; i < kFlagWords; i++) host[i] = 0;
     CUDA_TRY(cudaMemcpy(s.flags, host.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
+  return LBM_B200_OK;
+}
+
+// The one-step ring kernels keep only three planes of one halo row per side up to date; the two-steps-per-pass
+// kernel pulls from two full halo rows per side.  When it is switched on for a live ring, every slab fetches the
+// four rows from its neighbours' current buffers (all ranks idle: the caller's responsibility, as for set_cells).
+int pull_halos(lbm_b200* h)
+{
+  if (h->n_ranks == 1 || !h->connected || h->inplace) return LBM_B200_OK;
+  for (Slab& s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const size_t row_bytes = (size_t)h->nx * sizeof(float);
+    const float* so = s.south.buf[h->cur];
+    const float* no = s.north.buf[h->cur];
+    float* me = s.buf[h->cur];
+    for (int k = 0; k < 9; k++) {
+      const size_t mk = (size_t)k * s.plane, sk = (size_t)k * s.south.plane, nk = (size_t)k * s.north.plane;
+      CUDA_TRY(cudaMemcpyAsync(me + mk, so + sk + (size_t)s.south.rows * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 2) * h->nx, so + sk + (size_t)(s.south.rows - 1) * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 1) * h->nx, no + nk + (size_t)1 * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 3) * h->nx, no + nk + (size_t)2 * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
   }
   return LBM_B200_OK;
 }
@@ -778,6 +869,14 @@ static int create_whole(lbm_b200** handle, int nx, int ny, float density, float 
     }
     h->inv = 1.0f / ((long)nx * ny - blocked);
   }
+  if (n_slabs > 1) {
+    for (int i = 0; i < n_slabs; i++) {
+      const int f = first[i], r = rows[i];
+      rc = set_halo_mask(h, h->slabs[i], obstacles + (size_t)((f - 1 + ny) % ny) * nx, obstacles + (size_t)((f + r) % ny) * nx,
+                         obstacles + (size_t)((f - 2 + 2 * ny) % ny) * nx);
+      if (rc) { lbm_b200_destroy(h); return rc; }
+    }
+  }
   // ring wiring: direct peer pointers (d2q9-bgk.c:244-247 for the neighbour ranks)
   if (n_slabs > 1) {
     for (int i = 0; i < n_slabs; i++) {
@@ -885,6 +984,7 @@ int lbm_b200_ipc_export(lbm_b200* h, void* blob)
   CUDA_TRY(cudaIpcGetMemHandle(&b.buf[0], s.buf[0]));
   if (!h->inplace) CUDA_TRY(cudaIpcGetMemHandle(&b.buf[1], s.buf[1]));
   CUDA_TRY(cudaIpcGetMemHandle(&b.flags, s.flags));
+  CUDA_TRY(cudaIpcGetMemHandle(&b.mask, s.mask));
   b.plane = s.plane; b.rows = s.rows; b.device = s.device; b.pid = (int)getpid(); b.inplace = h->inplace ? 1 : 0;
   memcpy(blob, &b, sizeof b);
   return LBM_B200_OK;
@@ -894,6 +994,7 @@ static int open_neighbour(Neighbour& n, const IpcBlob& b)
 {
   for (int i = 0; i < (b.inplace ? 1 : 2); i++) CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
   CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
+  CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.mask, b.mask, cudaIpcMemLazyEnablePeerAccess));
   n.plane = (size_t)b.plane; n.rows = b.rows; n.ipc = true;
   return LBM_B200_OK;
 }
@@ -918,6 +1019,13 @@ int lbm_b200_ipc_connect(lbm_b200* h, const void* south_blob, const void* north_
   } else {
     rc = open_neighbour(s.north, nb);
     if (rc) return rc;
+  }
+  // obstacle words of the neighbours' rows this slab recomputes in the two-steps-per-pass kernel (set_halo_mask)
+  {
+    const size_t w = (size_t)h->mask_row_words, bytes = w * sizeof(uint32_t);
+    CUDA_TRY(cudaMemcpy(s.mask + (size_t)s.rows * w, s.south.mask + (size_t)(s.south.rows - 1) * w, bytes, cudaMemcpyDefault));
+    CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 1) * w, s.north.mask, bytes, cudaMemcpyDefault));
+    CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2) * w, s.south.mask + (size_t)(s.south.rows - 2) * w, bytes, cudaMemcpyDefault));
   }
   h->connected = true;
   return LBM_B200_OK;
@@ -971,6 +1079,19 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       CUDA_TRY(cudaGetLastError());
       h->launches++;
     }
+    if (h->fused2 && h->n_ranks > 1) {
+      // The slab north of the driven row's owner recomputes that owner's last row in the first step of a pass and
+      // pulls planes 5 and 6 of the driven row out of its own second halo row: its copy (planes 2,3,5,6,7, pushed
+      // un-forced at the end of the last run) gets the same pre-pass; same inputs, same bits.
+      for (Slab& s : h->slabs) {
+        if (s.first_row != 0) continue;
+        CUDA_TRY(cudaSetDevice(s.device));
+        lbm::accelerate_row<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
+            s.buf[h->cur], layout_of(h, s), s.mask + (size_t)(s.rows + 2) * h->mask_row_words, s.rows + 2, h->sc.aw1, h->sc.aw2);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      }
+    }
     int t = 0;
     if (h->resident) {
       // many steps per cooperative launch; the buffers swap roles inside the kernel
@@ -1009,14 +1130,18 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       const int n = std::min(kChunkSteps, iters - t);
       if (h->fused2) {
         // fused passes and the single-step tail use different grids: slots are summed over per_step entries
-        Slab& s = h->slabs[0];
-        CUDA_TRY(cudaMemsetAsync(s.partials, 0, (size_t)n * s.per_step * sizeof(double), s.stream));
+        for (Slab& s : h->slabs) {
+          CUDA_TRY(cudaSetDevice(s.device));
+          CUDA_TRY(cudaMemsetAsync(s.partials, 0, (size_t)n * s.per_step * sizeof(double), s.stream));
+        }
       }
       for (int i = 0; i < n; i++) {
         int rc;
         if (h->fused2 && i + 1 < n) {                  // steps t+i and t+i+1 in one pass over HBM
-          rc = enqueue_fused2(h, i, t + i + 1 != iters - 1);
+          rc = enqueue_fused2(h, i, t + i + 1 != iters - 1, false);
           i++;
+        } else if (h->fused2 && h->n_ranks > 1) {      // a ring's odd step: same strips, same handshake
+          rc = enqueue_fused2(h, i, t + i != iters - 1, true);
         } else {
           rc = enqueue_step(h, i, t + i != iters - 1);
         }
@@ -1134,13 +1259,15 @@ int lbm_b200_set_cells(lbm_b200* h, const float* cells)
     CUDA_TRY(cudaSetDevice(s.device));
     float* scratch = nullptr;
     int step = 0;
-    int rc = staging(h, s, row_floats * sizeof(float), s.rows + 2, &scratch, &step);
+    int rc = staging(h, s, row_floats * sizeof(float), s.rows + 4, &scratch, &step);
     if (rc) return rc;
-    // owned rows plus both halo rows, taken from the periodic global grid
-    for (int r0 = 0; r0 < s.rows + 2; r0 += step) {
-      const int n = std::min(step, s.rows + 2 - r0);
+    // owned rows plus the halo rows (padded rows 0, rows+1 and the second halo rows rows+2 = row -2, rows+3 = row
+    // rows+1 of the slab), taken from the periodic global grid
+    for (int r0 = 0; r0 < s.rows + 4; r0 += step) {
+      const int n = std::min(step, s.rows + 4 - r0);
       for (int r = r0; r < r0 + n; r++) {
-        const int gy = ((s.first_row + r - 1) % h->ny + h->ny) % h->ny;
+        const int y = (r <= s.rows + 1) ? r - 1 : (r == s.rows + 2 ? -2 : s.rows + 1);
+        const int gy = ((s.first_row + y) % h->ny + h->ny) % h->ny;
         CUDA_TRY(cudaMemcpyAsync(scratch + (size_t)(r - r0) * row_floats, cells + (size_t)gy * row_floats,
                                  row_floats * sizeof(float), cudaMemcpyHostToDevice, s.stream));
       }
@@ -1221,9 +1348,13 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   lbm_b200_sync(h);
   destroy_graphs(h);
   plan(h);
-  if (!strcmp(key, "kernel")) {
+  if (!strcmp(key, "kernel") || !strcmp(key, "fused2")) {
     int rc = resync_flags(h);
     if (rc) return rc;
+    if (h->fused2 && !strcmp(key, "fused2")) {
+      rc = pull_halos(h);
+      if (rc) return rc;
+    }
   }
   return ensure_partials(h);
 }
@@ -1265,6 +1396,7 @@ void lbm_b200_destroy(lbm_b200* h)
       for (int i = 0; i < 2; i++)
         if (n->buf[i]) cudaIpcCloseMemHandle(n->buf[i]);
       if (n->flags) cudaIpcCloseMemHandle(n->flags);
+      if (n->mask) cudaIpcCloseMemHandle(n->mask);
     }
     for (int b = 0; b < 2; b++)
       if (s.buf[b]) cudaFree(s.buf[b]);

@@ -652,9 +652,10 @@ constexpr int kStripOut = 120;    // owned columns per strip (30 lanes x 4)
 struct FusedArgs {
   int band_rows;        // rows per work item
   int bands, strips;
-  int accel_row;        // padded row of global row ny-2 (the first step always gets the second step's force folded in)
-  int fold_last;        // whether the second step folds the following step's force in
+  int accel_row;        // padded row of global row ny-2, or -1 (the first step always gets the second step's force)
+  int fold_last;        // whether the launch's last step folds the following step's force in
   int partial_stride;   // doubles between the two steps' partials
+  int south_rows, north_rows;   // owned rows of the ring neighbours (PEER)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
@@ -670,13 +671,40 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Ring slabs: one flag word per 120-column strip and direction, same protocol as warp_peer_wait/warp_peer_signal.
+__device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, int strip, int strips)
+{
+  const int lane = threadIdx.x & 31;
+  if (lane < 3) {
+    int c = strip - 1 + lane;
+    if (c < 0) c = strips - 1; else if (c >= strips) c = 0;
+    const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
+    while ((int)(ld_acquire_sys(flags + c) - need) < 0) __nanosleep(20);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void strip_signal(const StepArgs& a, unsigned* flags, int strip)
+{
+  __threadfence_system();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) st_release_sys(flags + strip, *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u);
+}
+
 // shared memory of one warp: a three-row ring of the six first-step planes the second step reads later (planes
 // 4,7,8 of a row are consumed straight from registers), one staging row filled by cp.async one row ahead of the
 // arithmetic, and the six end-lane scalars of that row
 constexpr int kRingPlanes = 6;                                   // ring order: planes 0, 1, 3, 2, 5, 6
 constexpr int kFusedWarpFloat4 = 3 * kRingPlanes * 32 + 9 * 32 + 2;   // + 2 float4 for the end-lane scalars
 
-template <int HINT>
+// PEER   = a slab of a multi-GPU ring.  Padded rows: 0 / rows+1 are the halo rows next to the slab, rows+2 / rows+3
+//          the second halo rows (the neighbours' rows one further away); obstacle words of the two adjacent
+//          neighbour rows follow the slab's own.  The first step is ALSO computed for the neighbours' edge rows
+//          (redundantly, from the two halo rows), so the second step of the slab's own edge rows needs no exchange
+//          in the middle of a pass.  Once per pass a strip pushes what the neighbour's next pass pulls: planes
+//          0,1,3 + 2,5,6 of its last row and 2,5,6 of the row below go north, 0,1,3 + 4,7,8 of its first row and
+//          4,7,8 of the row above go south -- 9 (+2) plane rows per direction and pair of steps.
+// SINGLE = one timestep only (the odd tail of a run on a ring): the first step's result is the output.
+template <int HINT, bool PEER, bool SINGLE>
 __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const FusedArgs g)
 {
   extern __shared__ float4 fused_smem[];
@@ -687,16 +715,22 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
-  const int rows = a.row_last;                               // owned padded rows are 1..rows, periodic in y
+  const int rows = a.row_last;                               // owned padded rows are 1..rows
   const int nx = a.nx;
   double acc1 = 0.0, acc2 = 0.0;
+
+  // padded row of the 0-based row y in [-2, rows+1]: halo rows on a ring, periodic otherwise
+  auto prow = [&](const int y) -> int {
+    if (PEER) return (y >= 0 && y < rows) ? y + 1 : (y == -1 ? 0 : (y == rows ? rows + 1 : (y == -2 ? rows + 2 : rows + 3)));
+    return (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
+  };
 
   const long nitems = (long)g.bands * g.strips;
   for (long item = (long)blockIdx.x * warps + warp; item < nitems; item += (long)gridDim.x * warps) {
     const int band = (int)(item / g.strips);
     const int strip = (int)(item - (long)band * g.strips);
     const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
-    const int ye = min(yb + g.band_rows, rows);
+    const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
     // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
     int gx = strip * kStripOut - 4 + 4 * lane;
     if (gx < 0) gx += nx;
@@ -707,15 +741,19 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     const uint32_t* const mask_x = a.mask + (gx >> 5);
     const int mask_shift = gx & 31;
 
-    // ---- asynchronous copy of what the first step of row y (0-based; -1 and `rows` wrap) pulls, into the
-    //      staging row; returns the row's obstacle word of this lane's columns (its bits are >> mask_shift) ----
+    if (PEER) {
+      // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
+      if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips);
+      if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips);
+    }
+
+    // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
+    //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
     auto issue = [&](const int y) -> unsigned {
-      const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
-      const int rs = (row == 1) ? rows : row - 1;
-      const int rn = (row == rows) ? 1 : row + 1;
+      const int row = prow(y);
       const float* pc = src + (size_t)row * nx;
-      const float* ps = src + (size_t)rs * nx;
-      const float* pn = src + (size_t)rn * nx;
+      const float* ps = src + (size_t)prow(y - 1) * nx;
+      const float* pn = src + (size_t)prow(y + 1) * nx;
       cp_async16(stage + 0 * 32 + lane, pc + 0 * P + gx);
       cp_async16(stage + 1 * 32 + lane, pc + 1 * P + gx);
       cp_async16(stage + 2 * 32 + lane, ps + 2 * P + gx);
@@ -735,14 +773,53 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         cp_async4(ends + 5, pn + 7 * P + xe);
       }
       cp_async_commit();
-      return __ldg(mask_x + (size_t)(row - 1) * a.mask_row_words);     // used a whole row later: no stall here
+      // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
+      const int mrow = PEER ? ((y < 0) ? rows : (y >= rows ? rows + 1 : y)) : row - 1;
+      return __ldg(mask_x + (size_t)mrow * a.mask_row_words);           // used a whole row later: no stall here
     };
 
-    // ---- first step of row y out of the staging row (bits = its obstacle bits); the six planes the second step
+    // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
+    auto emit = [&](const int y, float (&f)[4][9]) {
+      const size_t o = (size_t)(y + 1) * nx + gx;
+#pragma unroll
+      for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+      if (PEER) {
+        auto put = [&](float* base, size_t plane, int row, int k) {
+          *reinterpret_cast<float4*>(base + k * plane + (size_t)row * nx + gx) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+        };
+        if (y == 0) {                                        // the southern slab's halo row rows+1
+          const int r = g.south_rows + 1;
+          put(a.south_dst, a.south_plane, r, 0); put(a.south_dst, a.south_plane, r, 1); put(a.south_dst, a.south_plane, r, 3);
+          put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
+        }
+        if (y == 1) {                                        // its second halo row
+          const int r = g.south_rows + 3;
+          put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
+        }
+        if (y == rows - 1) {                                 // the northern slab's halo row 0
+          put(a.north_dst, a.north_plane, 0, 0); put(a.north_dst, a.north_plane, 0, 1); put(a.north_dst, a.north_plane, 0, 3);
+          put(a.north_dst, a.north_plane, 0, 2); put(a.north_dst, a.north_plane, 0, 5); put(a.north_dst, a.north_plane, 0, 6);
+        }
+        if (y == rows - 2) {                                 // its second halo row (planes 3 and 7 ride along: if this
+          const int r = g.north_rows + 2;                    // is the driven row, the neighbour's copy gets its own pre-pass)
+          put(a.north_dst, a.north_plane, r, 2); put(a.north_dst, a.north_plane, r, 5); put(a.north_dst, a.north_plane, r, 6);
+          put(a.north_dst, a.north_plane, r, 3); put(a.north_dst, a.north_plane, r, 7);
+        }
+      }
+    };
+    // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
+    auto publish = [&](const int y) {
+      if (PEER) {
+        if (y == 1) strip_signal(a, a.signal_south, strip);
+        if (y == rows - 1) strip_signal(a, a.signal_north, strip);
+      }
+    };
+
+    // ---- first step of row y out of the staging row (mword = its obstacle word); the six planes the second step
     //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
-    //      row y+1 is issued as soon as the staging row has been read; its obstacle bits are returned. ----
+    //      row y+1 is issued as soon as the staging row has been read; its obstacle word is returned. ----
     auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
-      const int row = (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
+      const int row = prow(y);
       cp_async_wait_all();
       float4 c[9];
 #pragma unroll
@@ -768,9 +845,9 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
       // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
       // flies during both steps' arithmetic
-      const unsigned bits_next = ahead ? issue(y + 1) : 0u;
+      const unsigned word_next = ahead ? issue(y + 1) : 0u;
       const unsigned bits = mword >> mask_shift;
-      const bool fold = (row == g.accel_row);
+      const bool fold = (SINGLE ? g.fold_last != 0 : true) && (row == g.accel_row);
       float u4 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -780,6 +857,11 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
       }
       if (owned && y >= yb && y < ye) acc1 += (double)u4;
+      if (SINGLE) {
+        if (owned) emit(y, f);
+        publish(y);
+        return word_next;
+      }
       __syncwarp();                                          // the slot's previous readers are done
       float4* out = ring + slot * (kRingPlanes * 32) + lane;
       out[0 * 32] = make_float4(f[0][0], f[1][0], f[2][0], f[3][0]);
@@ -791,7 +873,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       k4 = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
       k7 = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
       k8 = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
-      return bits_next;
+      return word_next;
     };
 
     // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
@@ -833,29 +915,36 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
       }
       acc2 += (double)u4;
-      const size_t o = (size_t)row * nx + gx;
-#pragma unroll
-      for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+      emit(y, f);
     };
 
-    // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
     float4 k4, k7, k8;
-    unsigned bits_s = issue(yb - 1);
-    unsigned bits_c = step1(yb - 1, bits_s, 0, true, k4, k7, k8);          // -> bits of row yb
-    unsigned bits_n = step1(yb, bits_c, 1, true, k4, k7, k8);              // -> bits of row yb+1
-    int s_s = 0, s_c = 1, s_n = 2;
-    for (int y = yb; y < ye; y++) {
-      const unsigned bits_nn = step1(y + 1, bits_n, s_n, y + 1 < ye, k4, k7, k8);
-      step2(y, bits_c, s_s, s_c, k4, k7, k8);
-      bits_c = bits_n; bits_n = bits_nn;
-      const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+    if (SINGLE) {
+      unsigned word = issue(yb);
+      for (int y = yb; y < ye; y++) word = step1(y, word, 0, y + 1 < ye, k4, k7, k8);
+    } else {
+      // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
+      const unsigned word_s = issue(yb - 1);
+      unsigned word_c = step1(yb - 1, word_s, 0, true, k4, k7, k8);        // -> word of row yb
+      unsigned word_n = step1(yb, word_c, 1, true, k4, k7, k8);            // -> word of row yb+1
+      int s_s = 0, s_c = 1, s_n = 2;
+      for (int y = yb; y < ye; y++) {
+        const unsigned word_nn = step1(y + 1, word_n, s_n, y + 1 < ye, k4, k7, k8);
+        step2(y, word_c, s_s, s_c, k4, k7, k8);
+        publish(y);
+        word_c = word_n; word_n = word_nn;
+        const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+      }
     }
     __syncwarp();
   }
 
   block_sum_to(acc1, a.partials + blockIdx.x);
-  __syncthreads();
-  block_sum_to(acc2, a.partials + g.partial_stride + blockIdx.x);
+  if (!SINGLE) {
+    __syncthreads();
+    block_sum_to(acc2, a.partials + g.partial_stride + blockIdx.x);
+  }
+  if (PEER) peer_advance_epoch(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1019,7 +1108,7 @@ __global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words,
   unsigned n = __popc(mine);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-  if (lane == 0 && n) atomicAdd(blocked_cells, (unsigned long long)n);
+  if (lane == 0 && n && blocked_cells) atomicAdd(blocked_cells, (unsigned long long)n);
 }
 
 // uniform initial state, every padded row (d2q9-bgk.c:880-902)

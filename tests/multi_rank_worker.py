@@ -22,6 +22,8 @@ def main(out_path):
     dist.init_process_group("gloo")
     inplace = os.environ.get("LBM_TEST_INPLACE") == "1"
     nx, ny, iters = 384, 16 * size + 3, 301 if inplace else 300   # in place: end in the shifted layout L1
+    if os.environ.get("LBM_TEST_FUSED2") == "1":
+        iters = 303                                               # pairs of steps and a one-step tail
     obstacles = random_obstacles(np.random.default_rng(77), ny, nx, 0.06)
     rows, first = pkg.decompose(ny, size)
     r, f = int(rows[rank]), int(first[rank])
@@ -30,6 +32,10 @@ def main(out_path):
     blobs = [None] * size
     dist.all_gather_object(blobs, sim.export_ipc())
     sim.connect_ipc(blobs[(rank - 1) % size], blobs[(rank + 1) % size])
+    if os.environ.get("LBM_TEST_FUSED2") == "1":
+        sim.set_option("band_rows", 8)
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
     dist.barrier()
     av = torch.from_numpy(sim.run(iters).copy())
     dist.barrier()

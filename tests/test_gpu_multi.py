@@ -38,6 +38,27 @@ def test_single_process_multi_device(pkg, oracle, n, inplace):
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_fused2_across_devices(pkg, oracle, n):
+    """Two timesteps per pass on a ring of real devices: two halo rows per side over NVLink, one strip-level flag
+    handshake per pass, an odd tail."""
+    need_gpus(pkg, n)
+    rng = np.random.default_rng(60 + n)
+    nx, ny, iters = 600, 9 * n + 3, 201
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    ref_av = oracle.run(ref, obstacles, iters + 30, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n) as sim:
+        sim.set_option("band_rows", 4)
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(iters), sim.run(30)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
 @pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("n", [2, 8])
 def test_graph_replay_across_devices(pkg, oracle, n, inplace):
@@ -59,7 +80,7 @@ def test_graph_replay_across_devices(pkg, oracle, n, inplace):
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
-@pytest.mark.parametrize("inplace", [False, True])
+@pytest.mark.parametrize("inplace", [False, True, "fused2"])
 @pytest.mark.parametrize("n", [2, 4, 8])
 def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
     """torchrun-style launch: n processes, CUDA IPC handles exchanged with torch.distributed."""
@@ -72,7 +93,8 @@ def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
-                         env={**os.environ, "LBM_TEST_INPLACE": "1" if inplace else "0"})
+                         env={**os.environ, "LBM_TEST_INPLACE": "1" if inplace is True else "0",
+                              "LBM_TEST_FUSED2": "1" if inplace == "fused2" else "0"})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     data = np.load(out)
     obstacles, cells = data["obstacles"], data["cells"]

@@ -420,3 +420,41 @@ def test_fused2_is_refused_where_it_does_not_apply(pkg):
     with pkg.Simulation(128, 12, DENSITY, ACCEL, OMEGA, ob) as sim:     # narrower than two strips: stays on kernel 2
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") != 5 and sim.get_option("fused2") == 0
+
+
+@pytest.mark.parametrize("iters", [2, 7, 12])
+@pytest.mark.parametrize("n_slabs,nx,ny,band", [(2, 256, 16, 64), (3, 360, 29, 4), (4, 244, 47, 5), (8, 600, 40, 64), (2, 1024, 9, 2)])
+def test_fused2_ring_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny, band, iters):
+    """Two timesteps per pass on a ring: every slab recomputes the first step of its neighbours' edge rows from two halo
+    rows per side, and pushes two rows per direction once per pass; odd step counts end with a one-step pass through
+    the same strips.  Ragged strips, bands of 2..64 rows, slabs of 4..24 rows, the driven row's copy in the first
+    slab's second halo row."""
+    rng = np.random.default_rng(n_slabs * 1000 + nx + iters)
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
+    obstacles[:, 0] = rng.random(ny) < 0.5
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    obstacles[ny - 2, :] = rng.random(nx) < 0.2
+    cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, : nx // 3, 3] = 1e-5
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        sim.set_option("band_rows", band)
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
+        sim.set_cells(cells0)
+        ref = assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
+        # a second run from the state the first one left (halo rows refreshed by its last pass), then back to the
+        # one-step kernels on the same ring
+        ref2 = ref.copy()
+        ref_av, ref_exact = oracle.run(ref2, obstacles, 5, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles), exact=True)
+        av = sim.run(5)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref2))
+        assert_av(av, ref_av, ref_exact)
+        sim.set_option("fused2", 0)
+        ref3 = ref2.copy()
+        oracle.run(ref3, obstacles, 3, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+        sim.run(3)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref3))
+        sim.set_option("fused2", 1)                          # and on again: the two halo rows per side are fetched afresh
+        oracle.run(ref3, obstacles, 4, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+        sim.run(4)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref3))
