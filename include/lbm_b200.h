@@ -150,7 +150,15 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
 
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
  *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit); reads back 3
- *                   when the resident variant of kernel 2 is in use and 4 on an in-place handle
+ *                   when the resident variant of kernel 2 is in use, 4 on an in-place handle and 5 when two
+ *                   timesteps are fused per pass ("fused2")
+ *   "fused2"        two timesteps per pass over HBM (kernel 5: the first step of a 120-column strip goes into a
+ *                   shared-memory ring, the second comes out of it; half the DRAM traffic per step, bit-identical
+ *                   results; ring slabs keep two halo rows per side and exchange once per pass).  1 = on where it
+ *                   applies (ping-pong handle, nx % 4 == 0, nx >= 240, >= 4 rows per slab), 0 = off, -1 = automatic
+ *                   (on from 2^22 cells per GPU).  Reads back whether it is in use; "kernel" then reads 5.
+ *                   On a multi-process ring set it on every rank while the ring is idle.
+ *   "band_rows"     rows per work item of kernel 5 (0 = automatic)
  *   "inplace"       read-only: 1 on a handle made by lbm_b200_create_inplace
  *   "staging_bytes" in-place handles: size of the device staging buffer that get_cells / set_cells /
  *                   get_final_state move the state through, in chunks of whole rows (default 256 MB)

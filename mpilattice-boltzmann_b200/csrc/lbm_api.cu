@@ -96,6 +96,7 @@ struct IpcBlob {
 constexpr int kMaxCtasPerSm = 128;      // upper bound of the oversubscribed grid, in CTAs per SM
 constexpr long kResidentAutoMinCells = 1L << 18;
 constexpr long kGraphAutoCells = 1L << 22;  // up to 2048^2: step kernel <= ~60 us, launch gaps matter
+constexpr long kFusedAutoMinCells = 1L << 22;   // per GPU: from 2048^2 the two-steps-per-pass kernel wins
 constexpr int kChunkSteps = 256;        // steps whose CTA partials are kept before one reduce launch
 constexpr size_t kBounceBytes = 256u << 20;   // staging buffer of in-place handles (state in/out goes through it in row chunks)
 
@@ -117,7 +118,7 @@ struct lbm_b200 {
   // options
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
-  long opt_fused2 = 0, opt_band_rows = 64;
+  long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
   bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
   int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
@@ -201,7 +202,10 @@ bool want_resident(const lbm_b200* h)
 // slab needs four rows (the driven row ny-2 must not be a row a neighbour recomputes).
 bool want_fused2(const lbm_b200* h)
 {
-  return h->opt_fused2 == 1 && !h->inplace && use_vec4(h) && h->nx >= 2 * lbm::kStripOut && h->ny / h->n_ranks >= 4;
+  if (h->opt_fused2 == 0 || h->inplace || !use_vec4(h) || h->nx < 2 * lbm::kStripOut || h->ny / h->n_ranks < 4) return false;
+  // measured (profiles/r01_fused2.md): 1.46x at 2048^2, 1.55x at 4096^2, 1.69x at 16384^2; slower at 1024^2, where a
+  // pass has too few strips x bands to fill the GPU
+  return h->opt_fused2 == 1 || (long)h->nx * h->ny / h->n_ranks >= kFusedAutoMinCells;
 }
 
 constexpr int kFusedWarps = 8;
@@ -216,8 +220,24 @@ void plan(lbm_b200* h)
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
     for (Slab& s : h->slabs) {
       // bands of ~band_rows rows, balanced; the first and the last band hold at least two rows (a ring slab pushes
-      // two rows per direction and publishes them from one work item)
-      int bands = std::max(1, (s.rows + (int)h->opt_band_rows - 1) / (int)h->opt_band_rows);
+      // two rows per direction and publishes them from one work item).  Automatic height: every item recomputes two
+      // rows, and the items run in waves of one per resident warp -- take the height with the cheapest
+      // waves x (rows + 2.5) (reproduces the measured optima: 16 at 2048^2, 64 at 4096^2 and 16384^2).
+      int want = (int)h->opt_band_rows;
+      if (want <= 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+        const long slots = (long)sms * 2 * kFusedWarps;
+        double best = 0;
+        for (int b : {8, 12, 16, 24, 32, 48, 64, 96, 128}) {
+          const int nb = (s.rows + b - 1) / b;
+          const int per_b = (s.rows + nb - 1) / nb;
+          const long waves = ((long)nb * h->fused_strips + slots - 1) / slots;
+          const double cost = (double)waves * (per_b + 2.5);
+          if (want <= 0 || cost < best) { best = cost; want = b; }
+        }
+      }
+      int bands = std::max(1, (s.rows + want - 1) / want);
       int per = (s.rows + bands - 1) / bands;
       while (bands > 1 && (per < 2 || s.rows - (bands - 1) * per < 2)) {
         bands--;
@@ -754,8 +774,8 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_MIN_CTAS")) h->opt_min_ctas = atol(e);
   if (const char* e = getenv("LBM_B200_CACHE_HINT")) h->opt_cache_hint = atol(e);
   if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
-  if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = atol(e) == 1;
-  if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(1L, atol(e));
+  if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
+  if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
 }
 
 }  // namespace
@@ -1330,10 +1350,10 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "resident must be -1, 0 or 1");
     h->opt_resident = value;
   } else if (!strcmp(key, "fused2")) {
-    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "fused2 must be 0 or 1");
+    if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "fused2 must be -1, 0 or 1");
     h->opt_fused2 = value;
   } else if (!strcmp(key, "band_rows")) {
-    if (value < 1 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 1..2^20");
+    if (value < 0 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 0 (automatic) .. 2^20");
     h->opt_band_rows = value;
   } else if (!strcmp(key, "staging_bytes")) {
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
@@ -1364,7 +1384,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
   if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->fused2 ? 5 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1)));
   else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
-  else if (!strcmp(key, "band_rows")) *value = h->opt_band_rows;
+  else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;

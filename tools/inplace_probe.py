@@ -14,9 +14,9 @@ slabs = int(os.environ.get("SLABS", 1))
 with pkg.Simulation(nx, ny, 0.1, 0.005, 1.85, pkg.decks.channel_obstacles(nx, ny), n_slabs=slabs, devices=[0] * slabs,
                     inplace=bool(int(os.environ.get("INPLACE", 1)))) as sim:
     sim.set_option("graph_steps", 0)
-    if int(os.environ.get("FUSED2", 0)):
-        sim.set_option("band_rows", int(os.environ.get("BAND", 64)))
-        sim.set_option("fused2", 1)
+    if not sim.get_option("inplace"):
+        sim.set_option("band_rows", int(os.environ.get("BAND", 0)))
+        sim.set_option("fused2", int(os.environ.get("FUSED2", 0)))
     sim.enqueue(steps)
     sim.sync()
     sim.enqueue(steps)

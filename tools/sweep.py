@@ -52,6 +52,8 @@ def main():
             if args.fused2:
                 sim.set_option("band_rows", band)
                 sim.set_option("fused2", 1)
+            elif not args.inplace:
+                sim.set_option("fused2", 0)
             sim.set_option("ctas_per_sm", per_sm)
             sim.set_option("cache_hint", hint)
             sim.set_option("graph_steps", graph)
