@@ -330,23 +330,27 @@ def bench_ours(args, pkg):
     # ---- e2e: a whole job through the C-ABI from host buffers ----------------------------
     fields_t = torch.empty((4, rows, nx), dtype=torch.float32).pin_memory()
     av_t = torch.empty(timesteps, dtype=torch.float32).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    sim = make_sim()                                  # H2D: this rank's obstacle rows (int per cell, packed on the device)
-    t1 = time.perf_counter()
-    sim.enqueue(timesteps)
-    sim.fetch_av_vels(timesteps, av_t.numpy())        # D2H: per-step averages (synchronises)
-    if args.inplace and distributed:
-        dist.barrier()                                # in place, edge-row populations may live in the neighbours' buffers
-    t2 = time.perf_counter()
-    sim.final_state(fields_t.numpy())                 # D2H: u_x, u_y, |u|, pressure
-    t3 = time.perf_counter()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_phases = {"create_s": round(t1 - t0, 4), "run_and_av_vels_s": round(t2 - t1, 4), "final_state_s": round(t3 - t2, 4)}
+    e2e_s, e2e_phases, pressure_ok = None, None, True
+    for _ in range(2):                                # best of two jobs: allocating 19 GB right after freeing it varies
+        barrier()
+        t0 = time.perf_counter()
+        sim = make_sim()                              # H2D: this rank's obstacle rows (int per cell, packed on the device)
+        t1 = time.perf_counter()
+        sim.enqueue(timesteps)
+        sim.fetch_av_vels(timesteps, av_t.numpy())    # D2H: per-step averages (synchronises)
+        if args.inplace and distributed:
+            dist.barrier()                            # in place, edge-row populations may live in the neighbours' buffers
+        t2 = time.perf_counter()
+        sim.final_state(fields_t.numpy())             # D2H: u_x, u_y, |u|, pressure
+        t3 = time.perf_counter()
+        barrier()
+        job_s = max_over_ranks(time.perf_counter() - t0)
+        pressure_ok = pressure_ok and bool(torch.isfinite(fields_t[3]).all())
+        sim.close()
+        if e2e_s is None or job_s < e2e_s:
+            e2e_s = job_s
+            e2e_phases = {"create_s": round(t1 - t0, 4), "run_and_av_vels_s": round(t2 - t1, 4), "final_state_s": round(t3 - t2, 4)}
     e2e_value = cells_global * timesteps / e2e_s / 1e6
-    pressure_ok = bool(torch.isfinite(fields_t[3]).all())
-    sim.close()
     if not pressure_ok:
         sys.exit("bench.py: e2e run produced a non-finite pressure field")
     h2d = 4 * nx * rows
@@ -365,7 +369,7 @@ def bench_ours(args, pkg):
             "e2e": {"value": round(e2e_value, 1), "unit": "MLUPS", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K,
                     "what": "lbm_b200_create (obstacle upload) + enqueue + fetch_av_vels + get_final_state into pinned "
-                            f"host memory, {timesteps} timesteps, wall clock, max over ranks",
+                            f"host memory, {timesteps} timesteps, wall clock, max over ranks, better of two jobs",
                     "phases_rank0": e2e_phases},
             "gpu_launches": int(launches) * n,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

@@ -727,8 +727,11 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
   const long nitems = (long)g.bands * g.strips;
   for (long item = (long)blockIdx.x * warps + warp; item < nitems; item += (long)gridDim.x * warps) {
-    const int band = (int)(item / g.strips);
+    int band = (int)(item / g.strips);
     const int strip = (int)(item - (long)band * g.strips);
+    // a ring slab does its two edge bands first: their halo rows are on the way to the neighbours (and published)
+    // while the interior bands run, as the reference overlaps its halo exchange with the interior rows (326-366)
+    if (PEER && g.bands > 2) band = (band == 0) ? 0 : (band == 1 ? g.bands - 1 : band - 1);
     const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
     const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
     // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
