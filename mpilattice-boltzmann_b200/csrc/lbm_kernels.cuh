@@ -672,9 +672,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Ring slabs: one flag word per 120-column strip and direction, same protocol as warp_peer_wait/warp_peer_signal.
-__device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, int strip, int strips)
+__device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, int strip, int strips, int lane)
 {
-  const int lane = threadIdx.x & 31;
   if (lane < 3) {
     int c = strip - 1 + lane;
     if (c < 0) c = strips - 1; else if (c >= strips) c = 0;
@@ -683,11 +682,11 @@ __device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* fl
   }
   __syncwarp();
 }
-__device__ __forceinline__ void strip_signal(const StepArgs& a, unsigned* flags, int strip)
+__device__ __forceinline__ void strip_signal(const StepArgs& a, unsigned* flags, int strip, int lane)
 {
   __threadfence_system();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) st_release_sys(flags + strip, *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u);
+  if (lane == 0) st_release_sys(flags + strip, *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u);
 }
 
 // shared memory of one warp: a three-row ring of the six first-step planes the second step reads later (planes
@@ -721,8 +720,9 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
   // padded row of the 0-based row y in [-2, rows+1]: halo rows on a ring, periodic otherwise
   auto prow = [&](const int y) -> int {
-    if (PEER) return (y >= 0 && y < rows) ? y + 1 : (y == -1 ? 0 : (y == rows ? rows + 1 : (y == -2 ? rows + 2 : rows + 3)));
-    return (y < 0) ? y + rows + 1 : ((y >= rows) ? y - rows + 1 : y + 1);
+    if ((unsigned)y < (unsigned)rows) return y + 1;         // an owned row: the common case
+    if (PEER) return y == -1 ? 0 : (y == rows ? rows + 1 : (y == -2 ? rows + 2 : rows + 3));
+    return (y < 0) ? y + rows + 1 : y - rows + 1;
   };
 
   const long nitems = (long)g.bands * g.strips;
@@ -746,8 +746,8 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
     if (PEER) {
       // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
-      if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips);
-      if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips);
+      if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips, lane);
+      if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips, lane);
     }
 
     // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       const size_t o = (size_t)(y + 1) * nx + gx;
 #pragma unroll
       for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
-      if (PEER) {
+      if (PEER && (y <= 1 || y >= rows - 2)) {
         auto put = [&](float* base, size_t plane, int row, int k) {
           *reinterpret_cast<float4*>(base + k * plane + (size_t)row * nx + gx) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
         };
@@ -812,9 +812,9 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     };
     // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
     auto publish = [&](const int y) {
-      if (PEER) {
-        if (y == 1) strip_signal(a, a.signal_south, strip);
-        if (y == rows - 1) strip_signal(a, a.signal_north, strip);
+      if (PEER && (y == 1 || y == rows - 1)) {
+        if (y == 1) strip_signal(a, a.signal_south, strip, lane);
+        if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
       }
     };
 

@@ -1,6 +1,6 @@
 #!/bin/bash
-# 8-GPU confirmation after the per-chunk handshake / ring graphs / in-place ring:
-# multi-GPU parity, weak N=8 (ping-pong and in place), strong N=4 and 8, the 1024^2 deck split over 8.
+# 8-GPU confirmation after fused2 (two timesteps per pass) became the default on rings too:
+# multi-GPU parity, weak N=8 (fused and one-step), strong N=8, the shipped decks split over 8.
 set -u
 OUT=${1:-gpurun_out/scale3}
 mkdir -p "$OUT"
@@ -12,8 +12,5 @@ run() { PORT=$((PORT + 1)); n=$1; sc=$2; shift 2; python -m torch.distributed.ru
 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline | tee -a "$OUT/weak.jsonl"
 run 8 weak | tee -a "$OUT/weak.jsonl"
 run 8 strong | tee -a "$OUT/strong.jsonl"
-run 4 strong | tee -a "$OUT/strong.jsonl"
-run 8 weak --inplace | tee -a "$OUT/weak_inplace.jsonl"
-LBM_B200_GRAPH_STEPS=100 run 8 strong | tee -a "$OUT/strong_graph100.jsonl"
+run 8 weak --fused2 0 | tee -a "$OUT/weak_onestep.jsonl"
 tools/deck_times.sh LBM_GPUS=8 | tee -a "$OUT/decks_8gpu.log"
-tools/deck_times.sh LBM_GPUS=4 | tail -1 | tee -a "$OUT/decks_8gpu.log"
