@@ -658,15 +658,14 @@ struct FusedArgs {
   int south_rows, north_rows;   // owned rows of the ring neighbours (PEER)
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+// (destination = a 32-bit shared-window address, converted once per kernel, not per copy)
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gmem)
 {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gmem)
 {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gmem) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_addr), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -711,6 +710,8 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
   float4* const ring = fused_smem + (size_t)warp * kFusedWarpFloat4;   // [3][6][32]
   float4* const stage = ring + 3 * kRingPlanes * 32;                   // [9][32]
   float* const ends = reinterpret_cast<float*>(stage + 9 * 32);        // [0..2] west (lane 0), [3..5] east (lane 31)
+  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage + lane);   // this lane's cell of staging plane 0
+  const unsigned ends_s = (unsigned)__cvta_generic_to_shared(ends);
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
@@ -752,33 +753,38 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
     // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
     //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
-    auto issue = [&](const int y) -> unsigned {
-      const int row = prow(y);
-      const float* pc = src + (size_t)row * nx;
-      const float* ps = src + (size_t)prow(y - 1) * nx;
-      const float* pn = src + (size_t)prow(y + 1) * nx;
-      cp_async16(stage + 0 * 32 + lane, pc + 0 * P + gx);
-      cp_async16(stage + 1 * 32 + lane, pc + 1 * P + gx);
-      cp_async16(stage + 2 * 32 + lane, ps + 2 * P + gx);
-      cp_async16(stage + 3 * 32 + lane, pc + 3 * P + gx);
-      cp_async16(stage + 4 * 32 + lane, pn + 4 * P + gx);
-      cp_async16(stage + 5 * 32 + lane, ps + 5 * P + gx);
-      cp_async16(stage + 6 * 32 + lane, ps + 6 * P + gx);
-      cp_async16(stage + 7 * 32 + lane, pn + 7 * P + gx);
-      cp_async16(stage + 8 * 32 + lane, pn + 8 * P + gx);
+    // (q_y = the row the next copy is for; q_s, q_c, q_n = the padded rows it pulls from, rolled forward per copy)
+    int q_y = SINGLE ? yb : yb - 1;
+    int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
+    auto issue = [&]() -> unsigned {
+      const float* pc = src + (size_t)q_c * nx;
+      const float* ps = src + (size_t)q_s * nx;
+      const float* pn = src + (size_t)q_n * nx;
+      cp_async16(stage_s + 0 * 512, pc + 0 * P + gx);
+      cp_async16(stage_s + 1 * 512, pc + 1 * P + gx);
+      cp_async16(stage_s + 2 * 512, ps + 2 * P + gx);
+      cp_async16(stage_s + 3 * 512, pc + 3 * P + gx);
+      cp_async16(stage_s + 4 * 512, pn + 4 * P + gx);
+      cp_async16(stage_s + 5 * 512, ps + 5 * P + gx);
+      cp_async16(stage_s + 6 * 512, ps + 6 * P + gx);
+      cp_async16(stage_s + 7 * 512, pn + 7 * P + gx);
+      cp_async16(stage_s + 8 * 512, pn + 8 * P + gx);
       if (lane == 0) {
-        cp_async4(ends + 0, pc + 1 * P + xw);
-        cp_async4(ends + 1, ps + 5 * P + xw);
-        cp_async4(ends + 2, pn + 8 * P + xw);
+        cp_async4(ends_s + 0, pc + 1 * P + xw);
+        cp_async4(ends_s + 4, ps + 5 * P + xw);
+        cp_async4(ends_s + 8, pn + 8 * P + xw);
       } else if (lane == 31) {
-        cp_async4(ends + 3, pc + 3 * P + xe);
-        cp_async4(ends + 4, ps + 6 * P + xe);
-        cp_async4(ends + 5, pn + 7 * P + xe);
+        cp_async4(ends_s + 12, pc + 3 * P + xe);
+        cp_async4(ends_s + 16, ps + 6 * P + xe);
+        cp_async4(ends_s + 20, pn + 7 * P + xe);
       }
       cp_async_commit();
       // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
-      const int mrow = PEER ? ((y < 0) ? rows : (y >= rows ? rows + 1 : y)) : row - 1;
-      return __ldg(mask_x + (size_t)mrow * a.mask_row_words);           // used a whole row later: no stall here
+      const int mrow = PEER ? ((q_y < 0) ? rows : (q_y >= rows ? rows + 1 : q_y)) : q_c - 1;
+      const unsigned word = __ldg(mask_x + (size_t)mrow * a.mask_row_words);   // used a whole row later: no stall here
+      q_y++;
+      q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
+      return word;
     };
 
     // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
@@ -822,7 +828,6 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
     //      row y+1 is issued as soon as the staging row has been read; its obstacle word is returned. ----
     auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
-      const int row = prow(y);
       cp_async_wait_all();
       float4 c[9];
 #pragma unroll
@@ -848,9 +853,9 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
       // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
       // flies during both steps' arithmetic
-      const unsigned word_next = ahead ? issue(y + 1) : 0u;
+      const unsigned word_next = ahead ? issue() : 0u;
       const unsigned bits = mword >> mask_shift;
-      const bool fold = (SINGLE ? g.fold_last != 0 : true) && (row == g.accel_row);
+      const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
       float u4 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -923,11 +928,11 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
     float4 k4, k7, k8;
     if (SINGLE) {
-      unsigned word = issue(yb);
+      unsigned word = issue();
       for (int y = yb; y < ye; y++) word = step1(y, word, 0, y + 1 < ye, k4, k7, k8);
     } else {
       // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
-      const unsigned word_s = issue(yb - 1);
+      const unsigned word_s = issue();
       unsigned word_c = step1(yb - 1, word_s, 0, true, k4, k7, k8);        // -> word of row yb
       unsigned word_n = step1(yb, word_c, 1, true, k4, k7, k8);            // -> word of row yb+1
       int s_s = 0, s_c = 1, s_n = 2;

@@ -8,7 +8,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
-nx = ny = int(os.environ.get("N", 16384))
+nx = int(os.environ.get("N", 16384))
+ny = int(os.environ.get("NY", nx))
 steps = int(os.environ.get("STEPS", 6))
 slabs = int(os.environ.get("SLABS", 1))
 with pkg.Simulation(nx, ny, 0.1, 0.005, 1.85, pkg.decks.channel_obstacles(nx, ny), n_slabs=slabs, devices=[0] * slabs,
