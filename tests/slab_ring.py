@@ -147,6 +147,76 @@ def run_slab_inplace(pkg, oracle, rank, size, nx, ny, iters, density, accel, ome
     return buf[1:rows + 1].copy(), av
 
 
+# ---- two timesteps per pass on a ring (csrc/lbm_kernels.cuh kernel 5): two halo rows per side, one exchange per pass ----
+def run_slab_fused2(pkg, oracle, rank, size, nx, ny, iters, density, accel, omega, obstacles, cells0):
+    """The fused protocol of the product with the oracle's stepper: per pass the slab computes the FIRST step also for
+    its neighbours' edge rows (from two halo rows per side), the SECOND step for its own rows, and then pushes exactly
+    the plane rows the neighbours' next pass pulls:
+        north: planes 0,1,3,2,5,6 of the last row, planes 2,5,6 (+3,7) of the row below it
+        south: planes 0,1,3,4,7,8 of the first row, planes 4,7,8 of the row above it
+    Everything else in the halo rows stays NaN.  An odd last step is a one-step pass with the same pushes.  The slab
+    north of the driven row's owner applies the body-force pre-pass to its copy of that row.
+    Array rows: index i <-> slab row i-2, i.e. [row -2, row -1, rows 0..R-1, row R, row R+1]."""
+    rows_all, first_all = pkg.decompose(ny, size)
+    R, first = int(rows_all[rank]), int(first_all[rank])
+    inv = pkg.free_cells_inv(obstacles)
+    south, north = (rank - 1) % size, (rank + 1) % size
+    gy = [(first + i - 2) % ny for i in range(R + 4)]
+    ob = np.ascontiguousarray(obstacles[gy])                    # obstacle rows incl. the neighbours' rows (static)
+    a = np.full((R + 4, nx, 9), np.nan, np.float32)
+    a[2:R + 2] = cells0[first:first + R]
+    accel_i = (ny - 2 - first) + 2 if first <= ny - 2 < first + R else -1      # array index of the driven row, if owned
+    copy_i = 0 if first == 0 and size > 1 else -1                               # rank 0 keeps a copy of it in row -2
+    av = np.zeros(iters, np.float32)
+
+    def exchange(state):
+        """pushes this slab's four edge rows into the neighbours' halo rows (only the planes their next pass pulls)"""
+        def pack(row, planes):
+            out = np.full((nx, 9), np.nan, np.float32)
+            out[:, planes] = state[row][:, planes]
+            return out
+        up = np.stack([pack(R + 1, [0, 1, 3, 2, 5, 6]), pack(R, [2, 5, 6, 3, 7])])       # last row, row below it
+        down = np.stack([pack(2, [0, 1, 3, 4, 7, 8]), pack(3, [4, 7, 8])])               # first row, row above it
+        from_south, from_north = swap_rows(up, down, rank, size)
+        state[1], state[0] = from_south[0], from_south[1]        # rows -1 and -2
+        state[R + 2], state[R + 3] = from_north[0], from_north[1]   # rows R and R+1
+
+    def force(state, i):
+        vals = np.ascontiguousarray(state[i])
+        oracle.accelerate_row(vals, ob[i], density, accel)
+        state[i] = vals
+
+    exchange(a)
+    t = 0
+    while t < iters:
+        # body force of the step that comes next (pre-pass of a run, or folded into the previous store): here always
+        # applied explicitly before the step, on the owner and on rank 0's copy
+        if accel_i > 0:
+            force(a, accel_i)
+        if copy_i >= 0:
+            force(a, copy_i)
+        b = np.full_like(a, np.nan)
+        src = a                                                  # NaN-poisoned: a pull of anything not pushed would show
+        if iters - t >= 2:
+            # first step: neighbours' edge rows (redundant) and own rows; only the own rows count for the average
+            oracle.slab_timestep(src, b, ob, 1, 2, omega)
+            av[t] = oracle.slab_timestep(src, b, ob, 2, R + 2, omega) * inv
+            oracle.slab_timestep(src, b, ob, R + 2, R + 3, omega)
+            if accel_i > 0:
+                force(b, accel_i)                                # the second step's force on the first step's result
+            c = np.full_like(a, np.nan)
+            av[t + 1] = oracle.slab_timestep(b, c, ob, 2, R + 2, omega) * inv
+            a = c
+            t += 2
+        else:
+            av[t] = oracle.slab_timestep(src, b, ob, 2, R + 2, omega) * inv
+            a = b
+            t += 1
+        a[0] = a[1] = a[R + 2] = a[R + 3] = np.nan
+        exchange(a)
+    return a[2:R + 2].copy(), av
+
+
 def worker(rank, size, port, args, out_queue, inplace=False):
     import os
     import sys
@@ -161,7 +231,8 @@ def worker(rank, size, port, args, out_queue, inplace=False):
     pkg = entry.load_package()
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
-        cells, av = (run_slab_inplace if inplace else run_slab)(pkg, oracle_lib, rank, size, *args)
+        runner = {False: run_slab, True: run_slab_inplace, "fused2": run_slab_fused2}[inplace]
+        cells, av = runner(pkg, oracle_lib, rank, size, *args)
         # the final reduction of the per-rank av_vels arrays (reference d2q9-bgk.c:396)
         total = torch.from_numpy(av.copy())
         dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)
