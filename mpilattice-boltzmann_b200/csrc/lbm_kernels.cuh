@@ -8,6 +8,7 @@
 // whole words.  Algorithmic traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include "lbm_cell.cuh"
@@ -719,13 +720,6 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
   const int nx = a.nx;
   double acc1 = 0.0, acc2 = 0.0;
 
-  // padded row of the 0-based row y in [-2, rows+1]: halo rows on a ring, periodic otherwise
-  auto prow = [&](const int y) -> int {
-    if ((unsigned)y < (unsigned)rows) return y + 1;         // an owned row: the common case
-    if (PEER) return y == -1 ? 0 : (y == rows ? rows + 1 : (y == -2 ? rows + 2 : rows + 3));
-    return (y < 0) ? y + rows + 1 : y - rows + 1;
-  };
-
   const long nitems = (long)g.bands * g.strips;
   for (long item = (long)blockIdx.x * warps + warp; item < nitems; item += (long)gridDim.x * warps) {
     int band = (int)(item / g.strips);
@@ -733,218 +727,232 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
     // a ring slab does its two edge bands first: their halo rows are on the way to the neighbours (and published)
     // while the interior bands run, as the reference overlaps its halo exchange with the interior rows (326-366)
     if (PEER && g.bands > 2) band = (band == 0) ? 0 : (band == 1 ? g.bands - 1 : band - 1);
-    const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
-    const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
-    // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
-    int gx = strip * kStripOut - 4 + 4 * lane;
-    if (gx < 0) gx += nx;
-    while (gx >= nx) gx -= nx;
-    const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
-    const int xw = (gx == 0) ? nx - 1 : gx - 1;
-    const int xe = (gx + 4 >= nx) ? 0 : gx + 4;
-    const uint32_t* const mask_x = a.mask + (gx >> 5);
-    const int mask_shift = gx & 31;
 
-    if (PEER) {
-      // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
-      if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips, lane);
-      if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips, lane);
-    }
+    // One work item.  EDGE (ring slabs only): the band touches the slab's first or last row -- halo rows, flag
+    // handshake and pushes; every other band of a ring slab runs exactly the single-GPU code.
+    auto run_item = [&](auto edge_tag) {
+      constexpr bool EDGE = decltype(edge_tag)::value;
+      // padded row of the 0-based row y in [-2, rows+1]: halo rows at a ring slab's edges, periodic otherwise
+      auto prow = [&](const int y) -> int {
+        if ((unsigned)y < (unsigned)rows) return y + 1;     // an owned row: the common case
+        if (EDGE) return y == -1 ? 0 : (y == rows ? rows + 1 : (y == -2 ? rows + 2 : rows + 3));
+        return (y < 0) ? y + rows + 1 : y - rows + 1;
+      };
+      const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
+      const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
+      // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
+      int gx = strip * kStripOut - 4 + 4 * lane;
+      if (gx < 0) gx += nx;
+      while (gx >= nx) gx -= nx;
+      const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
+      const int xw = (gx == 0) ? nx - 1 : gx - 1;
+      const int xe = (gx + 4 >= nx) ? 0 : gx + 4;
+      const uint32_t* const mask_x = a.mask + (gx >> 5);
+      const int mask_shift = gx & 31;
 
-    // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
-    //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
-    // (q_y = the row the next copy is for; q_s, q_c, q_n = the padded rows it pulls from, rolled forward per copy)
-    int q_y = SINGLE ? yb : yb - 1;
-    int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
-    auto issue = [&]() -> unsigned {
-      const float* pc = src + (size_t)q_c * nx;
-      const float* ps = src + (size_t)q_s * nx;
-      const float* pn = src + (size_t)q_n * nx;
-      cp_async16(stage_s + 0 * 512, pc + 0 * P + gx);
-      cp_async16(stage_s + 1 * 512, pc + 1 * P + gx);
-      cp_async16(stage_s + 2 * 512, ps + 2 * P + gx);
-      cp_async16(stage_s + 3 * 512, pc + 3 * P + gx);
-      cp_async16(stage_s + 4 * 512, pn + 4 * P + gx);
-      cp_async16(stage_s + 5 * 512, ps + 5 * P + gx);
-      cp_async16(stage_s + 6 * 512, ps + 6 * P + gx);
-      cp_async16(stage_s + 7 * 512, pn + 7 * P + gx);
-      cp_async16(stage_s + 8 * 512, pn + 8 * P + gx);
-      if (lane == 0) {
-        cp_async4(ends_s + 0, pc + 1 * P + xw);
-        cp_async4(ends_s + 4, ps + 5 * P + xw);
-        cp_async4(ends_s + 8, pn + 8 * P + xw);
-      } else if (lane == 31) {
-        cp_async4(ends_s + 12, pc + 3 * P + xe);
-        cp_async4(ends_s + 16, ps + 6 * P + xe);
-        cp_async4(ends_s + 20, pn + 7 * P + xe);
+      if (EDGE) {
+        // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
+        if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips, lane);
+        if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips, lane);
       }
-      cp_async_commit();
-      // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
-      const int mrow = PEER ? ((q_y < 0) ? rows : (q_y >= rows ? rows + 1 : q_y)) : q_c - 1;
-      const unsigned word = __ldg(mask_x + (size_t)mrow * a.mask_row_words);   // used a whole row later: no stall here
-      q_y++;
-      q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
-      return word;
-    };
 
-    // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
-    auto emit = [&](const int y, float (&f)[4][9]) {
-      const size_t o = (size_t)(y + 1) * nx + gx;
-#pragma unroll
-      for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
-      if (PEER && (y <= 1 || y >= rows - 2)) {
-        auto put = [&](float* base, size_t plane, int row, int k) {
-          *reinterpret_cast<float4*>(base + k * plane + (size_t)row * nx + gx) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
-        };
-        if (y == 0) {                                        // the southern slab's halo row rows+1
-          const int r = g.south_rows + 1;
-          put(a.south_dst, a.south_plane, r, 0); put(a.south_dst, a.south_plane, r, 1); put(a.south_dst, a.south_plane, r, 3);
-          put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
+      // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
+      //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
+      // (q_y = the row the next copy is for; q_s, q_c, q_n = the padded rows it pulls from, rolled forward per copy)
+      int q_y = SINGLE ? yb : yb - 1;
+      int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
+      auto issue = [&]() -> unsigned {
+        const float* pc = src + (size_t)q_c * nx;
+        const float* ps = src + (size_t)q_s * nx;
+        const float* pn = src + (size_t)q_n * nx;
+        cp_async16(stage_s + 0 * 512, pc + 0 * P + gx);
+        cp_async16(stage_s + 1 * 512, pc + 1 * P + gx);
+        cp_async16(stage_s + 2 * 512, ps + 2 * P + gx);
+        cp_async16(stage_s + 3 * 512, pc + 3 * P + gx);
+        cp_async16(stage_s + 4 * 512, pn + 4 * P + gx);
+        cp_async16(stage_s + 5 * 512, ps + 5 * P + gx);
+        cp_async16(stage_s + 6 * 512, ps + 6 * P + gx);
+        cp_async16(stage_s + 7 * 512, pn + 7 * P + gx);
+        cp_async16(stage_s + 8 * 512, pn + 8 * P + gx);
+        if (lane == 0) {
+          cp_async4(ends_s + 0, pc + 1 * P + xw);
+          cp_async4(ends_s + 4, ps + 5 * P + xw);
+          cp_async4(ends_s + 8, pn + 8 * P + xw);
+        } else if (lane == 31) {
+          cp_async4(ends_s + 12, pc + 3 * P + xe);
+          cp_async4(ends_s + 16, ps + 6 * P + xe);
+          cp_async4(ends_s + 20, pn + 7 * P + xe);
         }
-        if (y == 1) {                                        // its second halo row
-          const int r = g.south_rows + 3;
-          put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
-        }
-        if (y == rows - 1) {                                 // the northern slab's halo row 0
-          put(a.north_dst, a.north_plane, 0, 0); put(a.north_dst, a.north_plane, 0, 1); put(a.north_dst, a.north_plane, 0, 3);
-          put(a.north_dst, a.north_plane, 0, 2); put(a.north_dst, a.north_plane, 0, 5); put(a.north_dst, a.north_plane, 0, 6);
-        }
-        if (y == rows - 2) {                                 // its second halo row (planes 3 and 7 ride along: if this
-          const int r = g.north_rows + 2;                    // is the driven row, the neighbour's copy gets its own pre-pass)
-          put(a.north_dst, a.north_plane, r, 2); put(a.north_dst, a.north_plane, r, 5); put(a.north_dst, a.north_plane, r, 6);
-          put(a.north_dst, a.north_plane, r, 3); put(a.north_dst, a.north_plane, r, 7);
-        }
-      }
-    };
-    // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
-    auto publish = [&](const int y) {
-      if (PEER && (y == 1 || y == rows - 1)) {
-        if (y == 1) strip_signal(a, a.signal_south, strip, lane);
-        if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
-      }
-    };
+        cp_async_commit();
+        // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
+        const int mrow = EDGE ? ((q_y < 0) ? rows : (q_y >= rows ? rows + 1 : q_y)) : q_c - 1;
+        const unsigned word = __ldg(mask_x + (size_t)mrow * a.mask_row_words);   // used a whole row later: no stall here
+        q_y++;
+        q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
+        return word;
+      };
 
-    // ---- first step of row y out of the staging row (mword = its obstacle word); the six planes the second step
-    //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
-    //      row y+1 is issued as soon as the staging row has been read; its obstacle word is returned. ----
-    auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
-      cp_async_wait_all();
-      float4 c[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) c[k] = stage[k * 32 + lane];
-      const bool we = (lane == 0), ee = (lane == 31);
-      float e_c = 0.f, e_s = 0.f, e_n = 0.f;
-      if (we || ee) { e_c = ends[we ? 0 : 3]; e_s = ends[we ? 1 : 4]; e_n = ends[we ? 2 : 5]; }
-      const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
-      const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
-      const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
-      const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
-      const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
-      const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-      float f[4][9];
-      f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
-      f[0][1] = we ? e_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
-      f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
-      f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = ee ? e_c : dn3;
-      f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
-      f[0][5] = we ? e_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
-      f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = ee ? e_s : dn6;
-      f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = ee ? e_n : dn7;
-      f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-      // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
-      // flies during both steps' arithmetic
-      const unsigned word_next = ahead ? issue() : 0u;
-      const unsigned bits = mword >> mask_shift;
-      const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
-      float u4 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool blocked = (bits >> j) & 1u;
-        const float u = collide(f[j], blocked, a.c.omega);
-        u4 = (j == 0) ? u : add(u4, u);
-        if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-      }
-      if (owned && y >= yb && y < ye) acc1 += (double)u4;
-      if (SINGLE) {
-        if (owned) emit(y, f);
-        publish(y);
+      // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
+      auto emit = [&](const int y, float (&f)[4][9]) {
+        const size_t o = (size_t)(y + 1) * nx + gx;
+  #pragma unroll
+        for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+        if (EDGE && (y <= 1 || y >= rows - 2)) {
+          auto put = [&](float* base, size_t plane, int row, int k) {
+            *reinterpret_cast<float4*>(base + k * plane + (size_t)row * nx + gx) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+          };
+          if (y == 0) {                                        // the southern slab's halo row rows+1
+            const int r = g.south_rows + 1;
+            put(a.south_dst, a.south_plane, r, 0); put(a.south_dst, a.south_plane, r, 1); put(a.south_dst, a.south_plane, r, 3);
+            put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
+          }
+          if (y == 1) {                                        // its second halo row
+            const int r = g.south_rows + 3;
+            put(a.south_dst, a.south_plane, r, 4); put(a.south_dst, a.south_plane, r, 7); put(a.south_dst, a.south_plane, r, 8);
+          }
+          if (y == rows - 1) {                                 // the northern slab's halo row 0
+            put(a.north_dst, a.north_plane, 0, 0); put(a.north_dst, a.north_plane, 0, 1); put(a.north_dst, a.north_plane, 0, 3);
+            put(a.north_dst, a.north_plane, 0, 2); put(a.north_dst, a.north_plane, 0, 5); put(a.north_dst, a.north_plane, 0, 6);
+          }
+          if (y == rows - 2) {                                 // its second halo row (planes 3 and 7 ride along: if this
+            const int r = g.north_rows + 2;                    // is the driven row, the neighbour's copy gets its own pre-pass)
+            put(a.north_dst, a.north_plane, r, 2); put(a.north_dst, a.north_plane, r, 5); put(a.north_dst, a.north_plane, r, 6);
+            put(a.north_dst, a.north_plane, r, 3); put(a.north_dst, a.north_plane, r, 7);
+          }
+        }
+      };
+      // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
+      auto publish = [&](const int y) {
+        if (EDGE && (y == 1 || y == rows - 1)) {
+          if (y == 1) strip_signal(a, a.signal_south, strip, lane);
+          if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
+        }
+      };
+
+      // ---- first step of row y out of the staging row (mword = its obstacle word); the six planes the second step
+      //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
+      //      row y+1 is issued as soon as the staging row has been read; its obstacle word is returned. ----
+      auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
+        cp_async_wait_all();
+        float4 c[9];
+  #pragma unroll
+        for (int k = 0; k < 9; k++) c[k] = stage[k * 32 + lane];
+        const bool we = (lane == 0), ee = (lane == 31);
+        float e_c = 0.f, e_s = 0.f, e_n = 0.f;
+        if (we || ee) { e_c = ends[we ? 0 : 3]; e_s = ends[we ? 1 : 4]; e_n = ends[we ? 2 : 5]; }
+        const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+        const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+        const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+        const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+        const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+        const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+        float f[4][9];
+        f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+        f[0][1] = we ? e_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+        f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+        f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = ee ? e_c : dn3;
+        f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+        f[0][5] = we ? e_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+        f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = ee ? e_s : dn6;
+        f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = ee ? e_n : dn7;
+        f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+        // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
+        // flies during both steps' arithmetic
+        const unsigned word_next = ahead ? issue() : 0u;
+        const unsigned bits = mword >> mask_shift;
+        const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
+        float u4 = 0.f;
+  #pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const bool blocked = (bits >> j) & 1u;
+          const float u = collide(f[j], blocked, a.c.omega);
+          u4 = (j == 0) ? u : add(u4, u);
+          if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+        }
+        if (owned && y >= yb && y < ye) acc1 += (double)u4;
+        if (SINGLE) {
+          if (owned) emit(y, f);
+          publish(y);
+          return word_next;
+        }
+        __syncwarp();                                          // the slot's previous readers are done
+        float4* out = ring + slot * (kRingPlanes * 32) + lane;
+        out[0 * 32] = make_float4(f[0][0], f[1][0], f[2][0], f[3][0]);
+        out[1 * 32] = make_float4(f[0][1], f[1][1], f[2][1], f[3][1]);
+        out[2 * 32] = make_float4(f[0][3], f[1][3], f[2][3], f[3][3]);
+        out[3 * 32] = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
+        out[4 * 32] = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
+        out[5 * 32] = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
+        k4 = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
+        k7 = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
+        k8 = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
         return word_next;
-      }
-      __syncwarp();                                          // the slot's previous readers are done
-      float4* out = ring + slot * (kRingPlanes * 32) + lane;
-      out[0 * 32] = make_float4(f[0][0], f[1][0], f[2][0], f[3][0]);
-      out[1 * 32] = make_float4(f[0][1], f[1][1], f[2][1], f[3][1]);
-      out[2 * 32] = make_float4(f[0][3], f[1][3], f[2][3], f[3][3]);
-      out[3 * 32] = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
-      out[4 * 32] = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
-      out[5 * 32] = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
-      k4 = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
-      k7 = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
-      k8 = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
-      return word_next;
-    };
+      };
 
-    // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
-    //      row y (slot s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran ----
-    auto step2 = [&](const int y, const unsigned mword, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
-      const int row = y + 1;
-      __syncwarp();                                          // ring rows are complete
-      const float4* rs_ = ring + s_s * (kRingPlanes * 32) + lane;
-      const float4* rc_ = ring + s_c * (kRingPlanes * 32) + lane;
-      float4 c[9];
-      c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[2 * 32];
-      c[2] = rs_[3 * 32]; c[5] = rs_[4 * 32]; c[6] = rs_[5 * 32];
-      c[4] = k4; c[7] = k7; c[8] = k8;
-      const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
-      const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
-      const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
-      const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
-      const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
-      const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-      if (!owned) return;
-      float f[4][9];
-      f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
-      f[0][1] = up1;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
-      f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
-      f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = dn3;
-      f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
-      f[0][5] = up5;    f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
-      f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
-      f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
-      f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-      const unsigned bits = mword >> mask_shift;
-      const bool fold = g.fold_last && (row == g.accel_row);
-      float u4 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool blocked = (bits >> j) & 1u;
-        const float u = collide(f[j], blocked, a.c.omega);
-        u4 = (j == 0) ? u : add(u4, u);
-        if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-      }
-      acc2 += (double)u4;
-      emit(y, f);
-    };
+      // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
+      //      row y (slot s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran ----
+      auto step2 = [&](const int y, const unsigned mword, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
+        const int row = y + 1;
+        __syncwarp();                                          // ring rows are complete
+        const float4* rs_ = ring + s_s * (kRingPlanes * 32) + lane;
+        const float4* rc_ = ring + s_c * (kRingPlanes * 32) + lane;
+        float4 c[9];
+        c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[2 * 32];
+        c[2] = rs_[3 * 32]; c[5] = rs_[4 * 32]; c[6] = rs_[5 * 32];
+        c[4] = k4; c[7] = k7; c[8] = k8;
+        const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
+        const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
+        const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
+        const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
+        const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
+        const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+        if (!owned) return;
+        float f[4][9];
+        f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
+        f[0][1] = up1;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
+        f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
+        f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = dn3;
+        f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
+        f[0][5] = up5;    f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
+        f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
+        f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
+        f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+        const unsigned bits = mword >> mask_shift;
+        const bool fold = g.fold_last && (row == g.accel_row);
+        float u4 = 0.f;
+  #pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const bool blocked = (bits >> j) & 1u;
+          const float u = collide(f[j], blocked, a.c.omega);
+          u4 = (j == 0) ? u : add(u4, u);
+          if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
+        }
+        acc2 += (double)u4;
+        emit(y, f);
+      };
 
-    float4 k4, k7, k8;
-    if (SINGLE) {
-      unsigned word = issue();
-      for (int y = yb; y < ye; y++) word = step1(y, word, 0, y + 1 < ye, k4, k7, k8);
-    } else {
-      // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
-      const unsigned word_s = issue();
-      unsigned word_c = step1(yb - 1, word_s, 0, true, k4, k7, k8);        // -> word of row yb
-      unsigned word_n = step1(yb, word_c, 1, true, k4, k7, k8);            // -> word of row yb+1
-      int s_s = 0, s_c = 1, s_n = 2;
-      for (int y = yb; y < ye; y++) {
-        const unsigned word_nn = step1(y + 1, word_n, s_n, y + 1 < ye, k4, k7, k8);
-        step2(y, word_c, s_s, s_c, k4, k7, k8);
-        publish(y);
-        word_c = word_n; word_n = word_nn;
-        const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+      float4 k4, k7, k8;
+      if (SINGLE) {
+        unsigned word = issue();
+        for (int y = yb; y < ye; y++) word = step1(y, word, 0, y + 1 < ye, k4, k7, k8);
+      } else {
+        // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
+        const unsigned word_s = issue();
+        unsigned word_c = step1(yb - 1, word_s, 0, true, k4, k7, k8);        // -> word of row yb
+        unsigned word_n = step1(yb, word_c, 1, true, k4, k7, k8);            // -> word of row yb+1
+        int s_s = 0, s_c = 1, s_n = 2;
+        for (int y = yb; y < ye; y++) {
+          const unsigned word_nn = step1(y + 1, word_n, s_n, y + 1 < ye, k4, k7, k8);
+          step2(y, word_c, s_s, s_c, k4, k7, k8);
+          publish(y);
+          word_c = word_n; word_n = word_nn;
+          const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+        }
       }
-    }
-    __syncwarp();
+      __syncwarp();
+    };
+    if (PEER && (band == 0 || band == g.bands - 1)) run_item(std::true_type{});
+    else run_item(std::false_type{});
   }
 
   block_sum_to(acc1, a.partials + blockIdx.x);

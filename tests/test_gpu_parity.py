@@ -376,7 +376,8 @@ def test_switching_kernels_on_a_ring_keeps_the_handshake_consistent(pkg, oracle)
 
 # ---- two timesteps per pass over HBM (kernel 5, "fused2") -----------------------------------------------------------
 
-@pytest.mark.parametrize("nx,ny,band", [(256, 24, 64), (360, 19, 5), (244, 33, 7), (1024, 16, 4), (240, 9, 3), (2048, 40, 64)])
+@pytest.mark.parametrize("nx,ny,band", [(256, 24, 64), (360, 19, 5), (244, 33, 7), (1024, 16, 4), (240, 9, 3), (2048, 40, 64),
+                                        (256, 4, 0), (4096, 70, 0)])
 @pytest.mark.parametrize("iters", [2, 5, 16])
 def test_fused2_bit_exact(pkg, oracle, nx, ny, band, iters):
     """Pairs of timesteps fused into one pass (first step into a shared-memory ring, second step out of it): ragged last
@@ -390,8 +391,10 @@ def test_fused2_bit_exact(pkg, oracle, nx, ny, band, iters):
     cells0 = random_cells(rng, ny, nx)
     cells0[ny - 2, : nx // 3, 3] = 1e-5
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
-        sim.set_option("band_rows", band)
+        sim.set_option("band_rows", band)                       # 0 = automatic
         sim.set_option("fused2", 1)
+        if nx == 4096:
+            sim.set_option("ctas_per_sm", 1)                    # fewer CTAs than work items: the item loop strides
         assert sim.get_option("kernel") == 5
         sim.set_cells(cells0)
         assert_parity(sim, oracle, pkg, cells0, obstacles, iters)
