@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
       auto emit = [&](const int y, float (&f)[4][9]) {
         const size_t o = (size_t)(y + 1) * nx + gx;
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
         if (EDGE && (y <= 1 || y >= rows - 2)) {
           auto put = [&](float* base, size_t plane, int row, int k) {
@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
         cp_async_wait_all();
         float4 c[9];
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < 9; k++) c[k] = stage[k * 32 + lane];
         const bool we = (lane == 0), ee = (lane == 31);
         float e_c = 0.f, e_s = 0.f, e_n = 0.f;
@@ -861,14 +861,8 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         const unsigned word_next = ahead ? issue() : 0u;
         const unsigned bits = mword >> mask_shift;
         const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
-        float u4 = 0.f;
-  #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const bool blocked = (bits >> j) & 1u;
-          const float u = collide(f[j], blocked, a.c.omega);
-          u4 = (j == 0) ? u : add(u4, u);
-          if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-        }
+        const bool any_blocked = __any_sync(0xffffffffu, (bits & 0xFu) != 0u);
+        const float u4 = collide4(f, bits, any_blocked, a.c.omega, fold, a.c.aw1, a.c.aw2);
         if (owned && y >= yb && y < ye) acc1 += (double)u4;
         if (SINGLE) {
           if (owned) emit(y, f);
@@ -906,6 +900,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
         const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
         const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
+        const bool any_blocked = __any_sync(0xffffffffu, ((mword >> mask_shift) & 0xFu) != 0u);
         if (!owned) return;
         float f[4][9];
         f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
@@ -919,14 +914,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
         const unsigned bits = mword >> mask_shift;
         const bool fold = g.fold_last && (row == g.accel_row);
-        float u4 = 0.f;
-  #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const bool blocked = (bits >> j) & 1u;
-          const float u = collide(f[j], blocked, a.c.omega);
-          u4 = (j == 0) ? u : add(u4, u);
-          if (fold) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-        }
+        const float u4 = collide4(f, bits, any_blocked, a.c.omega, fold, a.c.aw1, a.c.aw2);
         acc2 += (double)u4;
         emit(y, f);
       };
