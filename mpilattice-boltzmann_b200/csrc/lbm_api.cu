@@ -1367,14 +1367,15 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   }
   lbm_b200_sync(h);
   destroy_graphs(h);
+  const bool was_fused = h->fused2;
   plan(h);
   if (!strcmp(key, "kernel") || !strcmp(key, "fused2")) {
     int rc = resync_flags(h);
     if (rc) return rc;
-    if (h->fused2 && !strcmp(key, "fused2")) {
-      rc = pull_halos(h);
-      if (rc) return rc;
-    }
+  }
+  if (h->fused2 && !was_fused) {           // whichever option brought the two-steps-per-pass kernel back on a ring
+    int rc = pull_halos(h);
+    if (rc) return rc;
   }
   return ensure_partials(h);
 }

@@ -461,3 +461,12 @@ def test_fused2_ring_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny,
         oracle.run(ref3, obstacles, 4, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
         sim.run(4)
         assert np.array_equal(bits(sim.get_cells()), bits(ref3))
+        sim.set_option("kernel", 1)                          # the scalar kernel switches it off implicitly ...
+        assert sim.get_option("fused2") == 0
+        oracle.run(ref3, obstacles, 3, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+        sim.run(3)
+        sim.set_option("kernel", 0)                          # ... and leaving it brings it back: halo rows fetched again
+        assert sim.get_option("fused2") == 1
+        oracle.run(ref3, obstacles, 4, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+        sim.run(4)
+        assert np.array_equal(bits(sim.get_cells()), bits(ref3))
