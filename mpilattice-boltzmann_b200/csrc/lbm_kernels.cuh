@@ -3,9 +3,18 @@
 // One timestep = ONE pass over the slab: pull-stream (propagate), bounce-back (rebound), BGK
 // collision, next step's accelerate_flow on row ny-2, and the block-level partial of
 // Sigma |m|/rho -- replacing reference d2q9-bgk.c:345-367.  Populations are nine fp32 planes
-// (structure of arrays) of (rows+2) x nx floats: padded row 0 and rows+1 are halo rows, rows
-// 1..rows are owned.  The obstacle map is 1 bit per cell, 32 cells per word, rows padded to
-// whole words.  Algorithmic traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
+// (structure of arrays) of (rows+4) x nx floats: padded row 0 and rows+1 are the halo rows next to the
+// slab, rows+2 / rows+3 the second halo rows (kernel 5 on a ring), rows 1..rows are owned.  The
+// obstacle map is 1 bit per cell, 32 cells per word, rows padded to whole words.  Algorithmic
+// traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
+//
+//   kernel 1  step_scalar     one cell per thread, any nx
+//   kernel 2  step_vec4       one warp per 128-cell row segment, 128-bit accesses + shuffles (0.976 of copy peak)
+//   kernel 3  steps_resident  kernel 2 in a cooperative many-steps-per-launch loop (launch-latency-bound grids)
+//   kernel 4  step_inplace    ONE buffer, AA access pattern (two alternating flavours)
+//   kernel 5  steps2_strip    TWO timesteps per pass over HBM through a shared-memory ring (default for big grids)
+// Ring slabs (multi-GPU): halo rows are stored straight into the neighbours' buffers over NVLink by the
+// step kernels themselves; flag words (one per 128-cell chunk / 120-column strip) order the exchange.
 #pragma once
 #include <cstdint>
 #include <type_traits>
