@@ -747,13 +747,16 @@ int finish_create(lbm_b200* h)
   return ensure_partials(h);
 }
 
-int check_common(int nx, int ny, float omega, const void* obstacles, lbm_b200** handle)
+// argument checks come before the device check, so that they can be exercised on a box without a GPU
+int check_common(int nx, int ny, float omega, const void* obstacles, lbm_b200** handle, bool inplace)
 {
   if (!handle) return fail(LBM_B200_ERR_ARG, "handle pointer is NULL");
   *handle = nullptr;
   if (!obstacles) return fail(LBM_B200_ERR_ARG, "obstacles pointer is NULL");
   if (nx < 4 || ny < 3) return fail(LBM_B200_ERR_ARG, "grid %dx%d too small (need nx >= 4, ny >= 3)", nx, ny);
   if (!(omega > 0.0f)) return fail(LBM_B200_ERR_ARG, "omega must be positive");
+  if (inplace && !(nx % 4 == 0 && nx >= 8))
+    return fail(LBM_B200_ERR_ARG, "in-place streaming needs nx %% 4 == 0 and nx >= 8 (got %d)", nx);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(LBM_B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
@@ -831,11 +834,9 @@ float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
 static int create_whole(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                         const int* obstacles, int n_slabs, const int* devices, bool inplace)
 {
-  int rc = check_common(nx, ny, omega, obstacles, handle);
+  int rc = check_common(nx, ny, omega, obstacles, handle, inplace);
   if (rc) return rc;
   if (n_slabs < 1) return fail(LBM_B200_ERR_ARG, "n_slabs must be >= 1");
-  if (inplace && !(nx % 4 == 0 && nx >= 8))
-    return fail(LBM_B200_ERR_ARG, "in-place streaming needs nx %% 4 == 0 and nx >= 8 (got %d)", nx);
   std::vector<int> rows(n_slabs), first(n_slabs);
   rc = lbm_b200_decompose(ny, n_slabs, rows.data(), first.data());
   if (rc) return rc;
@@ -942,10 +943,8 @@ static int create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, 
                        int rank, int n_ranks, float density, float accel, float omega,
                        float free_cells_inv, const int* obstacles_slab, int device, bool inplace)
 {
-  int rc = check_common(nx, ny_global, omega, obstacles_slab, handle);
+  int rc = check_common(nx, ny_global, omega, obstacles_slab, handle, inplace);
   if (rc) return rc;
-  if (inplace && !(nx % 4 == 0 && nx >= 8))
-    return fail(LBM_B200_ERR_ARG, "in-place streaming needs nx %% 4 == 0 and nx >= 8 (got %d)", nx);
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LBM_B200_ERR_ARG, "bad rank %d of %d", rank, n_ranks);
   if (rows < 3 || first_row < 0 || first_row + rows > ny_global) return fail(LBM_B200_ERR_ARG, "bad slab rows [%d, %d) of %d (at least 3 rows)", first_row, first_row + rows, ny_global);
   if (n_ranks == 1 && rows != ny_global) return fail(LBM_B200_ERR_ARG, "a single rank must own the whole grid");

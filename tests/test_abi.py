@@ -84,3 +84,7 @@ def test_bad_arguments_are_rejected_before_any_device_work(pkg):
         pkg.Simulation(2, 2, 0.1, 0.005, 1.85, np.zeros((2, 2), np.int32))
     with pytest.raises(ValueError):
         pkg.Simulation(16, 16, 0.1, 0.005, 1.85, np.zeros((8, 16), np.int32))
+    with pytest.raises(pkg.LBMError, match="nx % 4"):      # in-place streaming has no one-cell-per-thread kernel
+        pkg.Simulation(30, 9, 0.1, 0.005, 1.85, np.zeros((9, 30), np.int32), inplace=True)
+    with pytest.raises(pkg.LBMError, match="omega"):
+        pkg.Simulation(16, 16, 0.1, 0.005, 0.0, np.zeros((16, 16), np.int32))
