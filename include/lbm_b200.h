@@ -52,6 +52,12 @@ int lbm_b200_abi_version(void);
  * n_slabs entries.  Fails if any slab would get fewer than 3 rows. */
 int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row);
 
+/* Work decomposition of the two-timesteps-per-pass kernel (no counterpart in the reference; exposed so that it can
+ * be checked without a GPU): a slab of `rows` rows is cut into `*bands` bands of `*rows_per_band` rows -- the last
+ * one takes the remainder, and the first and the last hold at least two rows -- times ceil(nx / 120) column strips.
+ * band_rows = 0 picks the height automatically for a device with `sms` multiprocessors. */
+int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands, int* rows_per_band);
+
 /* 1.0f / (number of unblocked cells), replacing d2q9-bgk.c:805, 945-950. */
 float lbm_b200_free_cells_inv(const int* obstacles, long n_cells);
 

@@ -219,30 +219,10 @@ void plan(lbm_b200* h)
     h->resident = false;
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
     for (Slab& s : h->slabs) {
-      // bands of ~band_rows rows, balanced; the first and the last band hold at least two rows (a ring slab pushes
-      // two rows per direction and publishes them from one work item).  Automatic height: every item recomputes two
-      // rows, and the items run in waves of one per resident warp -- take the height with the cheapest
-      // waves x (rows + 2.5) (reproduces the measured optima: 16 at 2048^2, 64 at 4096^2 and 16384^2).
-      int want = (int)h->opt_band_rows;
-      if (want <= 0) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
-        const long slots = (long)sms * 2 * kFusedWarps;
-        double best = 0;
-        for (int b : {8, 12, 16, 24, 32, 48, 64, 96, 128}) {
-          const int nb = (s.rows + b - 1) / b;
-          const int per_b = (s.rows + nb - 1) / nb;
-          const long waves = ((long)nb * h->fused_strips + slots - 1) / slots;
-          const double cost = (double)waves * (per_b + 2.5);
-          if (want <= 0 || cost < best) { best = cost; want = b; }
-        }
-      }
-      int bands = std::max(1, (s.rows + want - 1) / want);
-      int per = (s.rows + bands - 1) / bands;
-      while (bands > 1 && (per < 2 || s.rows - (bands - 1) * per < 2)) {
-        bands--;
-        per = (s.rows + bands - 1) / bands;
-      }
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+      int bands = 1, per = s.rows;
+      lbm_b200_plan_bands(s.rows, h->nx, (int)h->opt_band_rows, sms, &bands, &per);
       s.fused_bands = bands;
       s.fused_band_rows = per;
       const long items = (long)h->fused_strips * bands;
@@ -820,6 +800,39 @@ int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row)
   for (int i = 0; i < n_slabs; i++)
     if (rows[i] < 3 && n_slabs > 1)
       return fail(LBM_B200_ERR_ARG, "slab %d of %d would have %d rows; at least 3 rows per slab are required", i, n_slabs, rows[i]);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands_out, int* rows_per_band)
+{
+  if (rows < 2 || nx < 4 || sms < 1 || band_rows < 0 || !bands_out || !rows_per_band)
+    return fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_plan_bands");
+  const int strips = (nx + lbm::kStripOut - 1) / lbm::kStripOut;
+  // Automatic height: every work item recomputes two rows, and the items run in waves of one per resident warp
+  // (2 CTAs x 8 warps per SM) -- take the height with the cheapest waves x (rows + 2.5); reproduces the measured
+  // optima (16 at 2048^2, 64 at 4096^2 and 16384^2, profiles/r01_fused2.md).
+  int want = band_rows;
+  if (want <= 0) {
+    const long slots = (long)sms * 16;
+    double best = 0;
+    for (int b : {8, 12, 16, 24, 32, 48, 64, 96, 128}) {
+      const int nb = (rows + b - 1) / b;
+      const int per_b = (rows + nb - 1) / nb;
+      const long waves = ((long)nb * strips + slots - 1) / slots;
+      const double cost = (double)waves * (per_b + 2.5);
+      if (want <= 0 || cost < best) { best = cost; want = b; }
+    }
+  }
+  // balanced bands; the first and the last one hold at least two rows (a ring slab pushes two rows per direction
+  // and publishes them from one work item)
+  int bands = std::max(1, (rows + want - 1) / want);
+  int per = (rows + bands - 1) / bands;
+  while (bands > 1 && (per < 2 || rows - (bands - 1) * per < 2)) {
+    bands--;
+    per = (rows + bands - 1) / bands;
+  }
+  *bands_out = bands;
+  *rows_per_band = per;
   return LBM_B200_OK;
 }
 

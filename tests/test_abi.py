@@ -88,3 +88,26 @@ def test_bad_arguments_are_rejected_before_any_device_work(pkg):
         pkg.Simulation(30, 9, 0.1, 0.005, 1.85, np.zeros((9, 30), np.int32), inplace=True)
     with pytest.raises(pkg.LBMError, match="omega"):
         pkg.Simulation(16, 16, 0.1, 0.005, 0.0, np.zeros((16, 16), np.int32))
+
+
+def test_band_plan_of_the_fused_kernel(pkg):
+    """Every row belongs to exactly one band, all bands but the last are equally tall, the first and the last hold
+    at least two rows (ring slabs push two rows per direction from one work item); the automatic height reproduces the
+    measured optima."""
+    lib = pkg.library()
+
+    def plan(rows, nx, want, sms=148):
+        bands, per = ctypes.c_int(), ctypes.c_int()
+        assert lib.lbm_b200_plan_bands(rows, nx, want, sms, ctypes.byref(bands), ctypes.byref(per)) == 0
+        return bands.value, per.value
+
+    for rows in list(range(2, 80)) + [127, 128, 129, 2048, 16384, 131076]:
+        for want in (0, 1, 2, 3, 5, 8, 64, 1000):
+            bands, per = plan(rows, 1024, want)
+            last = rows - (bands - 1) * per
+            assert bands >= 1 and per >= 1 and 0 < last <= max(per, rows)
+            if bands > 1:
+                assert per >= 2 and last >= 2, (rows, want, bands, per)
+    assert plan(2048, 2048, 0)[1] == 16 and plan(4096, 4096, 0)[1] == 64
+    assert plan(16384, 16384, 0)[1] in (64, 96)
+    assert lib.lbm_b200_plan_bands(1, 1024, 0, 148, None, None) != 0
