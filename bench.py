@@ -410,6 +410,7 @@ def main():
                     help="two timesteps per pass over HBM: 1 on, 0 off, default automatic (on from 2^22 cells per GPU)")
     ap.add_argument("--band-rows", dest="band_rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bit-exact multi-GPU parity check before the timed region")
     ap.add_argument("--inplace", action="store_true",
                     help="one population buffer per GPU, streamed in place (half the memory, same traffic)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",

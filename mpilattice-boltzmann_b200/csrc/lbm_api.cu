@@ -5,6 +5,7 @@
 // slab region per step, halo rows pushed over NVLink by the edge-row kernel itself, per-step
 // averages reduced on the device and copied back once.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include <unistd.h>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
@@ -43,11 +45,11 @@ int fail(int code, const char* fmt, ...)
                   __FILE__, __LINE__);                                                        \
   } while (0)
 
-enum FlagWord { kFromSouth = 0, kFromNorth = 1, kEpoch = 2, kDone = 3, kFlagWords = 32 };
+enum FlagWord { kFromSouth = 0, kFromNorth = 1, kEpoch = 2, kDone = 3, kError = 4, kFlagWords = 32 };
 
 struct Neighbour {
   float* buf[2] = {nullptr, nullptr};   // the neighbour's two population buffers (peer or IPC mapped)
-  uint32_t* mask = nullptr;             // the neighbour's obstacle words (only mapped while connecting)
+  uint32_t* mask = nullptr;             // the neighbour's obstacle words (read while connecting; stays mapped until destroy)
   unsigned* flags = nullptr;            // the neighbour's flag words
   size_t plane = 0;
   int rows = 0;
@@ -79,6 +81,7 @@ struct Slab {
   int threads_int = 256, grid_int = 0;
   int per_step = 1;
   int fused_grid = 0, fused_bands = 0, fused_band_rows = 0;   // two-steps-per-pass kernel (kernel 5)
+  bool fused_attr = false;              // its dynamic shared memory opt-in has been made on this slab's device
   std::vector<cudaGraphExec_t> graphs;  // [parity]
 };
 
@@ -119,6 +122,9 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
+  long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
+  long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
+  bool failed = false;                  // a wait timed out: the state is garbage, only destroy is valid
   bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
   int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
@@ -203,6 +209,11 @@ bool want_resident(const lbm_b200* h)
 bool want_fused2(const lbm_b200* h)
 {
   if (h->opt_fused2 == 0 || h->inplace || !use_vec4(h) || h->nx < 2 * lbm::kStripOut || h->ny / h->n_ranks < 4) return false;
+  // every slab of a ring needs 4 rows.  A whole-domain handle sees all of them; a one-slab-per-process handle sees
+  // its own and (once connected) its neighbours' -- lbm_b200_enqueue refuses to run the kernel on thinner slabs.
+  if (h->n_ranks > 1)
+    for (const Slab& s : h->slabs)
+      if (s.rows < 4) return false;
   // measured (profiles/r01_fused2.md): 1.46x at 2048^2, 1.55x at 4096^2, 1.69x at 16384^2; slower at 1024^2, where a
   // pass has too few strips x bands to fill the GPU
   return h->opt_fused2 == 1 || (long)h->nx * h->ny / h->n_ranks >= kFusedAutoMinCells;
@@ -262,6 +273,13 @@ void destroy_graphs(lbm_b200* h)
   }
   h->graph_len = 0;
 }
+
+// NVTX range over the enqueue of the timestep loop: what the reference brackets with
+// MPI_Pcontrol(1, "mainloop") ... MPI_Pcontrol(-1, "mainloop") (d2q9-bgk.c:276, 405) for its ITAC/TAU traces.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 double now_s()
 {
@@ -359,15 +377,20 @@ int set_halo_mask(lbm_b200* h, Slab& s, const int* row_m1, const int* row_p, con
   return LBM_B200_OK;
 }
 
-int ensure_av_capacity(Slab& s, size_t iters)
+// *moved = true when the array was reallocated: CUDA graphs captured reduce_partials with the old pointer and
+// must be rebuilt (the caller destroys them).
+int ensure_av_capacity(Slab& s, size_t iters, bool* moved)
 {
   const size_t need = std::max<size_t>(iters, 1);
   if (s.av_cap >= need) return LBM_B200_OK;
   CUDA_TRY(cudaSetDevice(s.device));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));        // nothing in flight may still write the old array
   if (s.av_dev) CUDA_TRY(cudaFree(s.av_dev));
-  s.av_dev = nullptr;
-  CUDA_TRY(cudaMalloc(&s.av_dev, need * sizeof(float)));
-  s.av_cap = need;
+  s.av_dev = nullptr; s.av_cap = 0;
+  const size_t cap = std::max(need, std::min<size_t>(2 * need, 1u << 20));   // room to grow without another move
+  CUDA_TRY(cudaMalloc(&s.av_dev, cap * sizeof(float)));
+  s.av_cap = cap;
+  *moved = true;
   return LBM_B200_OK;
 }
 
@@ -430,6 +453,8 @@ StepArgs base_args(const lbm_b200* h, const Slab& s, int slot, bool fold_accel)
   a.accel_row = fold_accel ? s.accel_row : -1;
   a.c = h->sc;
   a.partials = s.partials + (size_t)slot * s.per_step;
+  a.error = s.flags + kError;
+  a.timeout_ns = (unsigned long long)h->opt_spin_timeout_ms * 1000000ull;
   return a;
 }
 
@@ -531,6 +556,7 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
     // previous halo rows, push this state's halo rows over NVLink and signal; the interior follows in the
     // same launch while the neighbours consume (replaces MPI_Startall ... interior ... MPI_Waitall, 326-366)
     for (Slab& s : h->slabs) {
+      if (&s - h->slabs.data() == h->opt_debug_skip_slab) continue;
       CUDA_TRY(cudaSetDevice(s.device));
       StepArgs a = base_args(h, s, slot, fold_accel);
       a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
@@ -566,20 +592,28 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
 // Two timesteps in one pass over HBM (kernel 5): partial slots `slot` and `slot`+1 -- or, with `single`, the odd
 // last step of a run on a ring through the same strips (so that the strip-level handshake stays the only protocol
 // in use and the neighbours' two halo rows are refreshed).
+// The kernel needs more dynamic shared memory than the default limit: the opt-in is per device (context) and is
+// made once per slab when the kernel is first launched for it (Slab::fused_attr), never from process-global state.
+int allow_fused_smem(Slab& s)
+{
+  if (s.fused_attr) return LBM_B200_OK;
+  CUDA_TRY(cudaSetDevice(s.device));
+  const int bytes = (int)kFusedSmem;
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  s.fused_attr = true;
+  return LBM_B200_OK;
+}
+
 int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
 {
-  static bool attr_set[64] = {};
   for (Slab& s : h->slabs) {
+    if (&s - h->slabs.data() == h->opt_debug_skip_slab) continue;
     CUDA_TRY(cudaSetDevice(s.device));
-    if (s.device < 64 && !attr_set[s.device]) {
-      const int bytes = (int)kFusedSmem;
-      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      attr_set[s.device] = true;
-    }
+    if (int rc = allow_fused_smem(s)) return rc;
     StepArgs a = base_args(h, s, slot, false);
     a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
     a.south_of_first = s.rows;
@@ -750,6 +784,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   h->sc.omega = omega;
   h->sc.aw1 = density * accel * 0.111111111111111111111111f;    // d2q9-bgk.c:445
   h->sc.aw2 = density * accel * 0.0277777777777777777777778f;   // d2q9-bgk.c:446
+  h->sc.negzero = -0.0f;                                         // see lbm::mul2 (csrc/lbm_cell.cuh)
   h->mask_row_words = (nx + 31) / 32;
   if (const char* e = getenv("LBM_B200_KERNEL")) h->opt_kernel = atol(e);
   if (const char* e = getenv("LBM_B200_GRAPH_STEPS")) h->opt_graph_steps = atol(e);
@@ -838,10 +873,12 @@ int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands_out
 
 float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
 {
+  if (!obstacles || n_cells < 0) { fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_free_cells_inv"); return 0.0f; }
   long free_cells = n_cells;
   for (long i = 0; i < n_cells; i++)
     if (obstacles[i]) free_cells--;
-  return 1.0f / free_cells;
+  // a fully blocked grid gives +inf, exactly as the reference's 1.0f/numOfFreeCells would (d2q9-bgk.c:950)
+  return 1.0f / (float)free_cells;
 }
 
 static int create_whole(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
@@ -1022,12 +1059,46 @@ int lbm_b200_ipc_export(lbm_b200* h, void* blob)
   return LBM_B200_OK;
 }
 
+// unmaps whatever open_neighbour mapped (also after a partial failure)
+static void close_neighbour(Neighbour& n)
+{
+  if (n.ipc) {
+    for (int i = 0; i < 2; i++)
+      if (n.buf[i]) cudaIpcCloseMemHandle(n.buf[i]);
+    if (n.flags) cudaIpcCloseMemHandle(n.flags);
+    if (n.mask) cudaIpcCloseMemHandle(n.mask);
+  }
+  n = Neighbour{};
+}
+
 static int open_neighbour(Neighbour& n, const IpcBlob& b)
 {
+  n = Neighbour{};
+  n.ipc = true;                                     // from here on close_neighbour() releases what has been mapped
   for (int i = 0; i < (b.inplace ? 1 : 2); i++) CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
   CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
   CUDA_TRY(cudaIpcOpenMemHandle((void**)&n.mask, b.mask, cudaIpcMemLazyEnablePeerAccess));
-  n.plane = (size_t)b.plane; n.rows = b.rows; n.ipc = true;
+  n.plane = (size_t)b.plane; n.rows = b.rows;
+  return LBM_B200_OK;
+}
+
+// the part of lbm_b200_ipc_connect that can fail after mappings exist (the caller unmaps them on failure)
+static int connect_mapped(lbm_b200* h, Slab& s, const IpcBlob& sb, const IpcBlob& nb)
+{
+  int rc = open_neighbour(s.south, sb);
+  if (rc) return rc;
+  if (memcmp(&sb, &nb, sizeof sb) == 0) {           // two ranks: both neighbours are the same slab
+    s.north = s.south;
+    s.north.ipc = false;
+  } else {
+    rc = open_neighbour(s.north, nb);
+    if (rc) return rc;
+  }
+  // obstacle words of the neighbours' rows this slab recomputes in the two-steps-per-pass kernel (set_halo_mask)
+  const size_t w = (size_t)h->mask_row_words, bytes = w * sizeof(uint32_t);
+  CUDA_TRY(cudaMemcpy(s.mask + (size_t)s.rows * w, s.south.mask + (size_t)(s.south.rows - 1) * w, bytes, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 1) * w, s.north.mask, bytes, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2) * w, s.south.mask + (size_t)(s.south.rows - 2) * w, bytes, cudaMemcpyDefault));
   return LBM_B200_OK;
 }
 
@@ -1042,22 +1113,16 @@ int lbm_b200_ipc_connect(lbm_b200* h, const void* south_blob, const void* north_
   memcpy(&nb, north_blob, sizeof nb);
   if ((sb.inplace != 0) != h->inplace || (nb.inplace != 0) != h->inplace)
     return fail(LBM_B200_ERR_ARG, "ring neighbours must all be in-place handles or all ping-pong handles");
+  if (sb.rows < 3 || nb.rows < 3 || sb.plane != (unsigned long long)(sb.rows + 4) * h->nx || nb.plane != (unsigned long long)(nb.rows + 4) * h->nx)
+    return fail(LBM_B200_ERR_ARG, "a neighbour's blob does not describe a slab of this grid (nx %d)", h->nx);
   CUDA_TRY(cudaSetDevice(s.device));
-  int rc = open_neighbour(s.south, sb);
-  if (rc) return rc;
-  if (memcmp(&sb, &nb, sizeof sb) == 0) {           // two ranks: both neighbours are the same slab
-    s.north = s.south;
-    s.north.ipc = false;
-  } else {
-    rc = open_neighbour(s.north, nb);
-    if (rc) return rc;
-  }
-  // obstacle words of the neighbours' rows this slab recomputes in the two-steps-per-pass kernel (set_halo_mask)
-  {
-    const size_t w = (size_t)h->mask_row_words, bytes = w * sizeof(uint32_t);
-    CUDA_TRY(cudaMemcpy(s.mask + (size_t)s.rows * w, s.south.mask + (size_t)(s.south.rows - 1) * w, bytes, cudaMemcpyDefault));
-    CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 1) * w, s.north.mask, bytes, cudaMemcpyDefault));
-    CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2) * w, s.south.mask + (size_t)(s.south.rows - 2) * w, bytes, cudaMemcpyDefault));
+  const int rc = connect_mapped(h, s, sb, nb);
+  if (rc) {                                         // unmap what was mapped; g_error keeps the cause
+    if (!s.north.ipc) s.north = Neighbour{};        // an alias of the southern mapping (two ranks)
+    close_neighbour(s.north);
+    close_neighbour(s.south);
+    cudaGetLastError();
+    return rc;
   }
   h->connected = true;
   return LBM_B200_OK;
@@ -1068,14 +1133,23 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
   if (!h) return fail(LBM_B200_ERR_ARG, "NULL handle");
   if (iters < 0) return fail(LBM_B200_ERR_ARG, "iters must be >= 0");
   if (!h->connected) return fail(LBM_B200_ERR_STATE, "slab handle is not connected to its neighbours (lbm_b200_ipc_connect)");
+  if (h->failed) return fail(LBM_B200_ERR_STATE, "an earlier run gave up waiting for a ring neighbour; the state is invalid (destroy the handle)");
+  if (h->fused2 && h->n_ranks > 1)
+    for (const Slab& s : h->slabs)
+      if (s.rows < 4 || s.south.rows < 4 || s.north.rows < 4)
+        return fail(LBM_B200_ERR_STATE, "the two-steps-per-pass kernel needs at least 4 rows in every slab of a ring (this slab %d, "
+                    "south %d, north %d): set the option fused2 = 0 on every rank", s.rows, s.south.rows, s.north.rows);
+  NvtxRange nvtx_range("lbm_b200 mainloop");
   h->last_iters = iters;
   h->launches = 0;
+  bool av_moved = false;
   for (Slab& s : h->slabs) {
-    int rc = ensure_av_capacity(s, (size_t)iters);
+    int rc = ensure_av_capacity(s, (size_t)iters, &av_moved);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaMemsetAsync(s.cursor, 0, sizeof(unsigned), s.stream));
   }
+  if (av_moved) destroy_graphs(h);                   // they captured the old av_vels pointer
   int glen = (int)h->opt_graph_steps;
   if (h->resident || h->fused2) glen = 0;
   if (glen < 0) {
@@ -1118,8 +1192,14 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       for (Slab& s : h->slabs) {
         if (s.first_row != 0) continue;
         CUDA_TRY(cudaSetDevice(s.device));
-        lbm::accelerate_row<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
-            s.buf[h->cur], layout_of(h, s), s.mask + (size_t)(s.rows + 2) * h->mask_row_words, s.rows + 2, h->sc.aw1, h->sc.aw2);
+        // (ordered against the owner's push of that copy by the strip flags, not by streams: the owner may be
+        // another process whose last pass of the previous run is still in flight)
+        StepArgs a = base_args(h, s, 0, false);
+        peer_args(h, s, a);
+        a.wait_from_south = s.flags + kFlagWords;
+        lbm::accelerate_halo_row<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
+            s.buf[h->cur], layout_of(h, s), s.mask + (size_t)(s.rows + 2) * h->mask_row_words, s.rows + 2, h->sc.aw1, h->sc.aw2,
+            a, h->fused_strips);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
@@ -1198,6 +1278,24 @@ int lbm_b200_sync(lbm_b200* h)
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
   }
+  if (h->n_ranks > 1) {
+    // did a kernel give up waiting for a neighbour (lbm::spin_until)?  The reference would sit in MPI_Waitall
+    // (d2q9-bgk.c:364) for ever; here the run drains and the caller is told which exchange never arrived.
+    for (size_t i = 0; i < h->slabs.size(); i++) {
+      Slab& s = h->slabs[i];
+      unsigned err = 0;
+      CUDA_TRY(cudaSetDevice(s.device));
+      CUDA_TRY(cudaMemcpy(&err, s.flags + kError, sizeof err, cudaMemcpyDeviceToHost));
+      if (err) {
+        h->failed = true;
+        return fail(LBM_B200_ERR_STATE, "slab %d (rows %d..%d): gave up after %ld ms waiting for halo %s %u from the %s neighbour "
+                    "(rank %d); the neighbour is not running or the ranks enqueued different work",
+                    h->rank0 + (int)i, s.first_row, s.first_row + s.rows - 1, h->opt_spin_timeout_ms,
+                    h->fused2 ? "strip" : "chunk", err >> 8, (err & 3u) == lbm::kWaitFromSouth ? "southern" : "northern",
+                    ((err & 3u) == lbm::kWaitFromSouth ? h->rank0 + (int)i - 1 + h->n_ranks : h->rank0 + (int)i + 1) % h->n_ranks);
+      }
+    }
+  }
   return LBM_B200_OK;
 }
 
@@ -1220,6 +1318,7 @@ int lbm_b200_fetch_av_vels(lbm_b200* h, int iters, float* av_vels)
   if (!h || (!av_vels && iters > 0)) return fail(LBM_B200_ERR_ARG, "NULL argument");
   if (iters < 0 || iters > h->last_iters) return fail(LBM_B200_ERR_ARG, "iters exceeds the last enqueue");
   if (iters == 0) return LBM_B200_OK;
+  if (int rc = lbm_b200_sync(h)) return rc;          // drains the streams and reports a timed-out halo wait
   std::vector<float> part;
   for (size_t i = 0; i < h->slabs.size(); i++) {
     Slab& s = h->slabs[i];
@@ -1370,6 +1469,12 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "staging_bytes")) {
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
     h->opt_staging_bytes = value;
+  } else if (!strcmp(key, "spin_timeout_ms")) {
+    if (value < 1 || value > 3600000) return fail(LBM_B200_ERR_ARG, "spin_timeout_ms must be 1 .. 3600000");
+    h->opt_spin_timeout_ms = value;
+  } else if (!strcmp(key, "debug_skip_slab")) {
+    if (value < -1 || value >= (long)h->slabs.size()) return fail(LBM_B200_ERR_ARG, "debug_skip_slab must be -1 or a slab index of this handle");
+    h->opt_debug_skip_slab = value;
   } else if (!strcmp(key, "cache_hint")) {
     if (value < 0 || value > 4 || value == 3) return fail(LBM_B200_ERR_ARG, "cache_hint must be 0, 1, 2 or 4");
     if (h->inplace && value > 2) return fail(LBM_B200_ERR_ARG, "cache_hint of an in-place handle must be 0, 1 or 2");
@@ -1400,6 +1505,8 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
+  else if (!strcmp(key, "spin_timeout_ms")) *value = h->opt_spin_timeout_ms;
+  else if (!strcmp(key, "debug_skip_slab")) *value = h->opt_debug_skip_slab;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;
   else if (!strcmp(key, "ctas_per_sm")) *value = h->opt_ctas_per_sm;
   else if (!strcmp(key, "min_ctas")) *value = h->opt_min_ctas;
@@ -1424,13 +1531,9 @@ void lbm_b200_destroy(lbm_b200* h)
   }
   for (Slab& s : h->slabs) {
     cudaSetDevice(s.device);
-    for (Neighbour* n : {&s.south, &s.north}) {
-      if (!n->ipc) continue;
-      for (int i = 0; i < 2; i++)
-        if (n->buf[i]) cudaIpcCloseMemHandle(n->buf[i]);
-      if (n->flags) cudaIpcCloseMemHandle(n->flags);
-      if (n->mask) cudaIpcCloseMemHandle(n->mask);
-    }
+    if (!s.north.ipc) s.north = Neighbour{};        // peer pointers, or an alias of the southern IPC mapping
+    close_neighbour(s.north);
+    close_neighbour(s.south);
     for (int b = 0; b < 2; b++)
       if (s.buf[b]) cudaFree(s.buf[b]);
     if (s.mask) cudaFree(s.mask);

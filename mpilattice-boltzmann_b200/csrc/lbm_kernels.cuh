@@ -30,7 +30,7 @@ constexpr int kSegCells = 128;   // cells per warp work item in the vec4 kernel 
 struct StepArgs {
   const float* src;          // plane 0 of the source buffer
   float* dst;                // plane 0 of the destination buffer
-  size_t plane;              // floats between planes = (rows+2)*nx
+  size_t plane;              // floats between planes = (rows+4)*nx (two halo rows per side)
   const uint32_t* mask;      // bit-packed obstacles of the owned rows, row r at (r-1)*mask_row_words
   int mask_row_words;
   int nx;
@@ -51,6 +51,8 @@ struct StepArgs {
   unsigned* signal_north; unsigned* signal_south;
   unsigned* epoch;           // local: number of states this slab has published
   unsigned* done;            // local: CTA completion counter of this launch
+  unsigned* error;           // local: 0, or what a wait on a neighbour's flag gave up on (see spin_until)
+  unsigned long long timeout_ns;   // how long one wait may last before it gives up
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
@@ -64,14 +66,49 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Error word of a slab: (index of the chunk / strip waited for) << 8 | direction (1 = from the south, 2 = from the
+// north); 0 = no error.
+constexpr unsigned kWaitFromSouth = 1u, kWaitFromNorth = 2u;
+
+// Waits until *flag >= need (wrap-around compare).  Where the reference would hang for ever in MPI_Waitall
+// (d2q9-bgk.c:364) when a neighbour rank died, this wait is BOUNDED: after a.timeout_ns it records what it waited
+// for in the slab's error word and gives up; every later wait of the slab then returns at once, so that the work
+// already enqueued drains (producing garbage) and lbm_b200_sync can report LBM_B200_ERR_STATE instead of the GPU
+// spinning until it is reset.
+__device__ __noinline__ void spin_slow(const unsigned* flag, unsigned need, const StepArgs& a, unsigned code)
+{
+  volatile unsigned* err = a.error;
+  if (*err) return;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    for (int i = 0; i < 32; i++) {
+      if ((int)(ld_acquire_sys(flag) - need) >= 0) return;
+      __nanosleep(20);
+    }
+    if (*err) return;
+    if (global_ns() - t0 > a.timeout_ns) { atomicCAS(a.error, 0u, code); return; }
+  }
+}
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned need, const StepArgs& a, unsigned code)
+{
+  if ((int)(ld_acquire_sys(flag) - need) < 0) spin_slow(flag, need, a, code);
+}
+
 // Blocks until both ring neighbours have published the halo rows of the state this slab is
 // about to read (their flag >= this slab's epoch).  Replaces MPI_Waitall (d2q9-bgk.c:364).
 __device__ __forceinline__ void peer_wait(const StepArgs& a)
 {
   if (threadIdx.x == 0) {
     const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
-    while ((int)(ld_acquire_sys(a.wait_from_south) - need) < 0) __nanosleep(20);
-    while ((int)(ld_acquire_sys(a.wait_from_north) - need) < 0) __nanosleep(20);
+    spin_until(a.wait_from_south, need, a, kWaitFromSouth);
+    spin_until(a.wait_from_north, need, a, kWaitFromNorth);
   }
   __syncthreads();
 }
@@ -113,7 +150,7 @@ __device__ __forceinline__ void warp_peer_wait(const StepArgs& a, bool first, in
     if (c < 0) c = a.chunks - 1; else if (c >= a.chunks) c = 0;
     const unsigned* p = (first ? a.wait_from_south : a.wait_from_north) + c;
     const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
-    while ((int)(ld_acquire_sys(p) - need) < 0) __nanosleep(20);
+    spin_until(p, need, a, ((unsigned)c << 8) | (first ? kWaitFromSouth : kWaitFromNorth));
   }
   __syncwarp();
 }
@@ -291,8 +328,9 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
     const float w1v = west_edge ? e_c : up1, w5v = west_edge ? e_s : up5, w8v = west_edge ? e_n : up8;
     const float e3v = east_edge ? e_c : dn3, e6v = east_edge ? e_s : dn6, e7v = east_edge ? e_n : dn7;
 
+    const unsigned bits = active ? ((mw >> (x0 & 31)) & 0xFu) : 0u;
+    const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);   // warp-uniform: packed pairs where no lane is blocked
     if (active) {
-      const unsigned bits = (mw >> (x0 & 31)) & 0xFu;
       const bool fold_accel = (row == accel_row);
       float f[4][9];
       f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
@@ -305,15 +343,7 @@ __device__ __forceinline__ double vec4_pass(const StepArgs& a, const float* __re
       f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = e7v;
       f[0][8] = w8v;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
 
-      float u4 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool blocked = (bits >> j) & 1u;
-        const float u = collide(f[j], blocked, a.c.omega);
-        u4 = (j == 0) ? u : add(u4, u);
-        if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-      }
-      acc += (double)u4;
+      acc += (double)collide4(f, bits, any_blocked, a.c, fold_accel);
 
 #pragma unroll
       for (int k = 0; k < 9; k++)
@@ -419,6 +449,7 @@ __device__ __forceinline__ void inplace_segment(const StepArgs& a, float* __rest
   const size_t o_c = (size_t)row * a.nx;
   const unsigned bits = active ? ((__ldg(a.mask + (size_t)(row - 1) * a.mask_row_words + (x0 >> 5)) >> (x0 & 31)) & 0xFu) : 0u;
   const bool fold_accel = (row == accel_row);
+  const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
   float f[4][9];
 
   if (!NEIGHBOUR) {
@@ -428,15 +459,7 @@ __device__ __forceinline__ void inplace_segment(const StepArgs& a, float* __rest
         const float4 v = ld4_rw<HINT>(buf + (size_t)opposite(k) * P + o_c + x0);
         f[0][k] = v.x; f[1][k] = v.y; f[2][k] = v.z; f[3][k] = v.w;
       }
-      float u4 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool blocked = (bits >> j) & 1u;
-        const float u = collide(f[j], blocked, a.c.omega);
-        u4 = (j == 0) ? u : add(u4, u);
-        if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-      }
-      acc += (double)u4;
+      acc += (double)collide4(f, bits, any_blocked, a.c, fold_accel);
 #pragma unroll
       for (int k = 0; k < 9; k++)
         st4_rw<HINT>(buf + (size_t)k * P + o_c + x0, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
@@ -510,17 +533,7 @@ __device__ __forceinline__ void inplace_segment(const StepArgs& a, float* __rest
   f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = east_edge ? e_n : dn7;
   f[0][8] = west_edge ? w_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
 
-  if (active) {
-    float u4 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const bool blocked = (bits >> j) & 1u;
-      const float u = collide(f[j], blocked, a.c.omega);
-      u4 = (j == 0) ? u : add(u4, u);
-      if (fold_accel) accelerate(f[j], blocked, a.c.aw1, a.c.aw2);
-    }
-    acc += (double)u4;
-  }
+  if (active) acc += (double)collide4(f, bits, any_blocked, a.c, fold_accel);
   // the value that belongs to the neighbouring lane's aligned group of four: (slot 1, x-1) <- f3(x) etc.
   const float g3 = __shfl_down_sync(0xffffffffu, f[0][3], 1);
   const float g7 = __shfl_down_sync(0xffffffffu, f[0][7], 1);
@@ -655,7 +668,7 @@ __device__ __forceinline__ float* locate(const Layout& l, float* buf, int k, int
 //              loaded exactly once per strip, as in step_vec4 (128-bit loads + shuffles + end-lane scalars)
 //   step 2     row y needs step-1 rows y-1, y, y+1: 128-bit shared-memory loads + shuffles; lanes 1..30 own output
 // The arithmetic per cell and step is the same collide()/accelerate(): results are bit-identical to two launches
-// of step_vec4.  Single-slab handles only (a ring would need two halo rows).
+// of step_vec4.  Ring slabs keep two halo rows per side (template parameter PEER below).
 // ---------------------------------------------------------------------------------------
 constexpr int kStripOut = 120;    // owned columns per strip (30 lanes x 4)
 
@@ -681,13 +694,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Ring slabs: one flag word per 120-column strip and direction, same protocol as warp_peer_wait/warp_peer_signal.
-__device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, int strip, int strips, int lane)
+__device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, unsigned dir, int strip, int strips, int lane)
 {
   if (lane < 3) {
     int c = strip - 1 + lane;
     if (c < 0) c = strips - 1; else if (c >= strips) c = 0;
     const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
-    while ((int)(ld_acquire_sys(flags + c) - need) < 0) __nanosleep(20);
+    spin_until(flags + c, need, a, ((unsigned)c << 8) | dir);
   }
   __syncwarp();
 }
@@ -761,8 +774,8 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
       if (EDGE) {
         // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
-        if (yb == 0) strip_wait(a, a.wait_from_south, strip, g.strips, lane);
-        if (ye == rows) strip_wait(a, a.wait_from_north, strip, g.strips, lane);
+        if (yb == 0) strip_wait(a, a.wait_from_south, kWaitFromSouth, strip, g.strips, lane);
+        if (ye == rows) strip_wait(a, a.wait_from_north, kWaitFromNorth, strip, g.strips, lane);
       }
 
       // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
@@ -871,7 +884,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         const unsigned bits = mword >> mask_shift;
         const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
         const bool any_blocked = __any_sync(0xffffffffu, (bits & 0xFu) != 0u);
-        const float u4 = collide4(f, bits, any_blocked, a.c.omega, fold, a.c.aw1, a.c.aw2);
+        const float u4 = collide4(f, bits, any_blocked, a.c, fold);
         if (owned && y >= yb && y < ye) acc1 += (double)u4;
         if (SINGLE) {
           if (owned) emit(y, f);
@@ -923,7 +936,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
         const unsigned bits = mword >> mask_shift;
         const bool fold = g.fold_last && (row == g.accel_row);
-        const float u4 = collide4(f, bits, any_blocked, a.c.omega, fold, a.c.aw1, a.c.aw2);
+        const float u4 = collide4(f, bits, any_blocked, a.c, fold);
         acc2 += (double)u4;
         emit(y, f);
       };
@@ -1075,6 +1088,33 @@ __global__ void accelerate_row(float* buf, Layout l, const uint32_t* mask_row, i
     *p3 = sub(f3, aw1);
     *p6 = sub(f6, aw2);
     *p7 = sub(f7, aw2);
+  }
+}
+
+// The same pre-pass for the copy of the driven row that the slab NORTH of its owner keeps in its second halo row
+// (kernel 5 on a ring).  That copy is pushed by the owner during the last pass of the previous run, and nothing but
+// the strip flags orders that push against this kernel (the owner may be another process on another GPU whose
+// stream is still draining): every thread first waits until the strip that covers its column has been published
+// (flag >= this slab's epoch, exactly the condition the next pass's edge items wait for).
+__global__ void accelerate_halo_row(float* buf, Layout l, const uint32_t* mask_row, int row, float aw1, float aw2,
+                                    const StepArgs a, int strips)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= l.nx) return;
+  const int c = min(x / kStripOut, strips - 1);
+  const unsigned need = *reinterpret_cast<volatile unsigned*>(a.epoch);
+  spin_until(a.wait_from_south + c, need, a, ((unsigned)c << 8) | kWaitFromSouth);
+  const bool blocked = (mask_row[x >> 5] >> (x & 31)) & 1u;
+  float* p = buf + (size_t)row * l.nx + x;          // always the canonical layout (ping-pong handles only)
+  const size_t P = l.plane;
+  const float f3 = __ldcg(p + 3 * P), f6 = __ldcg(p + 6 * P), f7 = __ldcg(p + 7 * P);
+  if (!blocked && sub(f3, aw1) > 0.0f && sub(f6, aw2) > 0.0f && sub(f7, aw2) > 0.0f) {
+    p[1 * P] = add(__ldcg(p + 1 * P), aw1);
+    p[5 * P] = add(__ldcg(p + 5 * P), aw2);
+    p[8 * P] = add(__ldcg(p + 8 * P), aw2);
+    p[3 * P] = sub(f3, aw1);
+    p[6 * P] = sub(f6, aw2);
+    p[7 * P] = sub(f7, aw2);
   }
 }
 
