@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 enum {
   LBM_B200_OK = 0,
@@ -87,6 +87,19 @@ int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float acce
 int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                             const int* obstacles, int n_slabs, const int* devices);
 
+/* Obstacle map formats of the _ex constructors.  The reference keeps one int per cell (d2q9-bgk.c:875), which at
+ * 16384 x 16384 is a 1.07 GB upload for a 33 MB mask; callers that build their map themselves can hand it over in a
+ * denser form:
+ *   LBM_B200_OBST_INT32  int per cell, non-zero = blocked (the reference's layout; what the plain constructors take)
+ *   LBM_B200_OBST_UINT8  one byte per cell, non-zero = blocked
+ *   LBM_B200_OBST_BITS   one bit per cell: rows padded to whole 32-bit words ((nx + 31) / 32 per row), cell x of a
+ *                        row is bit (x & 31) of word (x >> 5); padding bits are ignored */
+enum { LBM_B200_OBST_INT32 = 0, LBM_B200_OBST_UINT8 = 1, LBM_B200_OBST_BITS = 2 };
+
+/* lbm_b200_create / lbm_b200_create_inplace (inplace != 0) with the obstacle map in any of the formats above. */
+int lbm_b200_create_ex(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                       const void* obstacles, int obstacles_format, int n_slabs, const int* devices, int inplace);
+
 /* ---- one slab per process (one rank per GPU; ranks launched by torchrun or similar) --- */
 
 /* As lbm_b200_create, for the slab [first_row, first_row + rows) of a ny_global-row grid owned
@@ -103,6 +116,11 @@ int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row
 int lbm_b200_create_slab_inplace(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
                                  int rank, int n_ranks, float density, float accel, float omega,
                                  float free_cells_inv, const int* obstacles_slab, int device);
+
+/* lbm_b200_create_slab / lbm_b200_create_slab_inplace (inplace != 0) with the slab's obstacle rows in any format. */
+int lbm_b200_create_slab_ex(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                            int rank, int n_ranks, float density, float accel, float omega,
+                            float free_cells_inv, const void* obstacles_slab, int obstacles_format, int device, int inplace);
 
 /* Size in bytes of the blob written by lbm_b200_ipc_export. */
 int lbm_b200_ipc_blob_bytes(void);

@@ -35,6 +35,13 @@ SIGNATURES = {
     "lbm_b200_create_slab": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                             ctypes.c_float, ctypes.c_float, c_int_p, ctypes.c_int]),
+    "lbm_b200_create_ex": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_int_p,
+                                          ctypes.c_int]),
+    "lbm_b200_create_slab_ex": (ctypes.c_int, [ctypes.POINTER(handle_t), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                               ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int]),
     "lbm_b200_ipc_blob_bytes": (ctypes.c_int, []),
     "lbm_b200_ipc_export": (ctypes.c_int, [handle_t, ctypes.c_void_p]),
     "lbm_b200_ipc_connect": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_void_p]),

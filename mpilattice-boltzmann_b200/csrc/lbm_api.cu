@@ -122,6 +122,7 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
+  long opt_prefetch_rows = 3;           // kernel 5: L2 prefetch distance in rows
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
   long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
   bool failed = false;                  // a wait timed out: the state is garbage, only destroy is valid
@@ -297,11 +298,44 @@ size_t flag_word_count(int nx)
   return kFlagWords + 2 * std::max(chunks, strips);
 }
 
-int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
+// bytes of `rows` obstacle rows in the caller's format
+size_t obstacle_row_bytes(const lbm_b200* h, int format)
+{
+  return format == LBM_B200_OBST_INT32 ? (size_t)h->nx * sizeof(int)
+         : format == LBM_B200_OBST_UINT8 ? (size_t)h->nx
+                                         : (size_t)h->mask_row_words * sizeof(uint32_t);
+}
+
+// Uploads `rows` obstacle rows (host, any of the three formats) and leaves them bit-packed at `mask_dst`; `staged`
+// is device scratch of at least rows * obstacle_row_bytes.  Counts the blocked cells into *blocked (may be NULL).
+int upload_mask(lbm_b200* h, Slab& s, const void* obstacles_rows, int format, int rows, void* staged, uint32_t* mask_dst,
+                unsigned long long* blocked)
+{
+  const size_t bytes = (size_t)rows * obstacle_row_bytes(h, format);
+  const long warps = (long)rows * ((h->mask_row_words + 31) / 32);
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  if (format == LBM_B200_OBST_BITS) {
+    CUDA_TRY(cudaMemcpyAsync(mask_dst, obstacles_rows, bytes, cudaMemcpyHostToDevice, s.stream));
+    const long words = (long)rows * h->mask_row_words;
+    lbm::adopt_mask_bits<<<(unsigned)((words + 255) / 256), 256, 0, s.stream>>>(mask_dst, h->nx, rows, h->mask_row_words, blocked);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(staged, obstacles_rows, bytes, cudaMemcpyHostToDevice, s.stream));
+    if (format == LBM_B200_OBST_INT32)
+      lbm::pack_mask<<<blocks, 256, 0, s.stream>>>(static_cast<const int*>(staged), h->nx, rows, h->mask_row_words, mask_dst, blocked);
+    else
+      lbm::pack_mask_u8<<<blocks, 256, 0, s.stream>>>(static_cast<const unsigned char*>(staged), h->nx, rows, h->mask_row_words, mask_dst, blocked);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return LBM_B200_OK;
+}
+
+int alloc_slab(lbm_b200* h, Slab& s, const void* obstacles_rows, int format)
 {
   const bool trace = getenv("LBM_B200_TRACE") != nullptr;
   const double t0 = now_s();
   CUDA_TRY(cudaSetDevice(s.device));
+  if ((unsigned long long)(s.rows + 4) * (unsigned long long)h->nx >= (1ull << 32))
+    return fail(LBM_B200_ERR_ARG, "a slab of %d x %d cells is too large: offsets inside a plane are 32-bit (use more slabs)", h->nx, s.rows);
   // padded rows: 0 and rows+1 are the halo rows next to the slab, rows+2 / rows+3 the second halo rows (the
   // southern / northern neighbour's row one further away; used by the two-steps-per-pass kernel on a ring)
   s.plane = (size_t)(s.rows + 4) * h->nx;
@@ -322,22 +356,19 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
   CUDA_TRY(cudaEventCreate(&s.ev_stop));
 
   const double t1 = now_s();
-  // obstacle rows: upload the reference's int-per-cell array into the (still unused) second population
-  // buffer and bit-pack it on the device: 32 cells per word, rows padded to whole words
+  // obstacle rows: the reference's int-per-cell array (or one byte per cell) is uploaded into the (still unused)
+  // second population buffer and bit-packed on the device -- 32 cells per word, rows padded to whole words; rows
+  // that arrive bit-packed go straight into place
   // (three more rows of words follow the slab's own: the neighbours' rows -1, `rows` and -2, see set_halo_mask)
   const size_t words = (size_t)(s.rows + 3) * h->mask_row_words;
-  const size_t cells = (size_t)s.rows * h->nx;
   CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
   CUDA_TRY(cudaMemsetAsync(s.mask, 0, std::max<size_t>(words, 1) * sizeof(uint32_t), s.stream));
-  int* staged = reinterpret_cast<int*>(s.buf[h->inplace ? 0 : 1]);   // 4 of the buffer's 36 bytes per cell
-  CUDA_TRY(cudaMemcpyAsync(staged, obstacles_rows, cells * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaMalloc(&s.blocked_dev, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(s.blocked_dev, 0, sizeof(unsigned long long), s.stream));
   {
-    const long warps = (long)s.rows * ((h->mask_row_words + 31) / 32);
-    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-    CUDA_TRY(cudaMalloc(&s.blocked_dev, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(s.blocked_dev, 0, sizeof(unsigned long long), s.stream));
-    lbm::pack_mask<<<blocks, 256, 0, s.stream>>>(staged, h->nx, s.rows, h->mask_row_words, s.mask, s.blocked_dev);
-    CUDA_TRY(cudaGetLastError());
+    void* staged = s.buf[h->inplace ? 0 : 1];        // at most 4 of the buffer's 36 bytes per cell
+    int rc = upload_mask(h, s, obstacles_rows, format, s.rows, staged, s.mask, s.blocked_dev);
+    if (rc) return rc;
   }
 
   if (trace) cudaStreamSynchronize(s.stream);
@@ -360,20 +391,20 @@ int alloc_slab(lbm_b200* h, Slab& s, const int* obstacles_rows)
 // Obstacle words of the three neighbour rows a ring slab computes redundantly in the two-steps-per-pass kernel:
 // word row `rows` = the southern neighbour's last row (y = -1), rows+1 = the northern neighbour's first row
 // (y = rows), rows+2 = the southern neighbour's second-to-last row (y = -2, only for the body-force pre-pass).
-int set_halo_mask(lbm_b200* h, Slab& s, const int* row_m1, const int* row_p, const int* row_m2)
+int set_halo_mask(lbm_b200* h, Slab& s, const void* row_m1, const void* row_p, const void* row_m2, int format)
 {
   CUDA_TRY(cudaSetDevice(s.device));
-  int* staged = nullptr;
-  CUDA_TRY(cudaMalloc(&staged, 3 * (size_t)h->nx * sizeof(int)));
-  const int* src[3] = {row_m1, row_p, row_m2};
-  for (int i = 0; i < 3; i++)
-    CUDA_TRY(cudaMemcpyAsync(staged + (size_t)i * h->nx, src[i], (size_t)h->nx * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-  const long warps = 3L * ((h->mask_row_words + 31) / 32);
-  lbm::pack_mask<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s.stream>>>(staged, h->nx, 3, h->mask_row_words,
-                                                                           s.mask + (size_t)s.rows * h->mask_row_words, nullptr);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s.stream));
-  CUDA_TRY(cudaFree(staged));
+  const size_t row_bytes = obstacle_row_bytes(h, format);
+  char* staged = nullptr;
+  CUDA_TRY(cudaMalloc(&staged, 3 * row_bytes));
+  const void* src[3] = {row_m1, row_p, row_m2};
+  int rc = LBM_B200_OK;
+  for (int i = 0; i < 3 && rc == LBM_B200_OK; i++)
+    rc = upload_mask(h, s, src[i], format, 1, staged + (size_t)i * row_bytes, s.mask + (size_t)(s.rows + i) * h->mask_row_words, nullptr);
+  cudaError_t e = cudaStreamSynchronize(s.stream);
+  cudaFree(staged);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(LBM_B200_ERR_CUDA, "uploading the neighbours' obstacle rows failed: %s", cudaGetErrorString(e));
   return LBM_B200_OK;
 }
 
@@ -625,6 +656,7 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
     g.accel_row = s.accel_row;
     g.fold_last = fold_last ? 1 : 0;
     g.partial_stride = s.per_step;
+    g.prefetch_rows = (int)h->opt_prefetch_rows;
     const dim3 grid(s.fused_grid), block(kFusedWarps * 32);
     if (h->n_ranks == 1) {
       if (h->opt_cache_hint == 1) lbm::steps2_strip<1, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
@@ -794,6 +826,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
   if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
+  if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
 }
 
 }  // namespace
@@ -882,10 +915,11 @@ float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
 }
 
 static int create_whole(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
-                        const int* obstacles, int n_slabs, const int* devices, bool inplace)
+                        const void* obstacles, int format, int n_slabs, const int* devices, bool inplace)
 {
   int rc = check_common(nx, ny, omega, obstacles, handle, inplace);
   if (rc) return rc;
+  if (format < LBM_B200_OBST_INT32 || format > LBM_B200_OBST_BITS) return fail(LBM_B200_ERR_ARG, "unknown obstacle format %d", format);
   if (n_slabs < 1) return fail(LBM_B200_ERR_ARG, "n_slabs must be >= 1");
   std::vector<int> rows(n_slabs), first(n_slabs);
   rc = lbm_b200_decompose(ny, n_slabs, rows.data(), first.data());
@@ -922,8 +956,10 @@ static int create_whole(lbm_b200** handle, int nx, int ny, float density, float 
       s.own_stream = true;
     }
   }
+  const size_t ob_row = obstacle_row_bytes(h, format);
+  const char* const ob = static_cast<const char*>(obstacles);
   for (int i = 0; i < n_slabs; i++) {
-    rc = alloc_slab(h, h->slabs[i], obstacles + (size_t)first[i] * nx);
+    rc = alloc_slab(h, h->slabs[i], ob + (size_t)first[i] * ob_row, format);
     if (rc) { lbm_b200_destroy(h); return rc; }
   }
   // 1/free cells (d2q9-bgk.c:945-950) from the blocked-cell counts the packing kernels produced
@@ -943,8 +979,8 @@ static int create_whole(lbm_b200** handle, int nx, int ny, float density, float 
   if (n_slabs > 1) {
     for (int i = 0; i < n_slabs; i++) {
       const int f = first[i], r = rows[i];
-      rc = set_halo_mask(h, h->slabs[i], obstacles + (size_t)((f - 1 + ny) % ny) * nx, obstacles + (size_t)((f + r) % ny) * nx,
-                         obstacles + (size_t)((f - 2 + 2 * ny) % ny) * nx);
+      rc = set_halo_mask(h, h->slabs[i], ob + (size_t)((f - 1 + ny) % ny) * ob_row, ob + (size_t)((f + r) % ny) * ob_row,
+                         ob + (size_t)((f - 2 + 2 * ny) % ny) * ob_row, format);
       if (rc) { lbm_b200_destroy(h); return rc; }
     }
   }
@@ -980,21 +1016,28 @@ static int create_whole(lbm_b200** handle, int nx, int ny, float density, float 
 int lbm_b200_create(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                     const int* obstacles, int n_slabs, const int* devices)
 {
-  return create_whole(handle, nx, ny, density, accel, omega, obstacles, n_slabs, devices, false);
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, LBM_B200_OBST_INT32, n_slabs, devices, false);
 }
 
 int lbm_b200_create_inplace(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
                             const int* obstacles, int n_slabs, const int* devices)
 {
-  return create_whole(handle, nx, ny, density, accel, omega, obstacles, n_slabs, devices, true);
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, LBM_B200_OBST_INT32, n_slabs, devices, true);
+}
+
+int lbm_b200_create_ex(lbm_b200** handle, int nx, int ny, float density, float accel, float omega,
+                       const void* obstacles, int obstacles_format, int n_slabs, const int* devices, int inplace)
+{
+  return create_whole(handle, nx, ny, density, accel, omega, obstacles, obstacles_format, n_slabs, devices, inplace != 0);
 }
 
 static int create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
                        int rank, int n_ranks, float density, float accel, float omega,
-                       float free_cells_inv, const int* obstacles_slab, int device, bool inplace)
+                       float free_cells_inv, const void* obstacles_slab, int format, int device, bool inplace)
 {
   int rc = check_common(nx, ny_global, omega, obstacles_slab, handle, inplace);
   if (rc) return rc;
+  if (format < LBM_B200_OBST_INT32 || format > LBM_B200_OBST_BITS) return fail(LBM_B200_ERR_ARG, "unknown obstacle format %d", format);
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LBM_B200_ERR_ARG, "bad rank %d of %d", rank, n_ranks);
   if (rows < 3 || first_row < 0 || first_row + rows > ny_global) return fail(LBM_B200_ERR_ARG, "bad slab rows [%d, %d) of %d (at least 3 rows)", first_row, first_row + rows, ny_global);
   if (n_ranks == 1 && rows != ny_global) return fail(LBM_B200_ERR_ARG, "a single rank must own the whole grid");
@@ -1018,7 +1061,7 @@ static int create_slab(lbm_b200** handle, int nx, int ny_global, int first_row, 
     return fail(LBM_B200_ERR_CUDA, "cannot create a stream on device %d", device);
   }
   s.own_stream = true;
-  rc = alloc_slab(h, s, obstacles_slab);
+  rc = alloc_slab(h, s, obstacles_slab, format);
   if (!rc) rc = finish_create(h);
   if (rc) { lbm_b200_destroy(h); return rc; }
   *handle = h;
@@ -1030,7 +1073,7 @@ int lbm_b200_create_slab(lbm_b200** handle, int nx, int ny_global, int first_row
                          float free_cells_inv, const int* obstacles_slab, int device)
 {
   return create_slab(handle, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
-                     obstacles_slab, device, false);
+                     obstacles_slab, LBM_B200_OBST_INT32, device, false);
 }
 
 int lbm_b200_create_slab_inplace(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
@@ -1038,7 +1081,15 @@ int lbm_b200_create_slab_inplace(lbm_b200** handle, int nx, int ny_global, int f
                                  float free_cells_inv, const int* obstacles_slab, int device)
 {
   return create_slab(handle, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
-                     obstacles_slab, device, true);
+                     obstacles_slab, LBM_B200_OBST_INT32, device, true);
+}
+
+int lbm_b200_create_slab_ex(lbm_b200** handle, int nx, int ny_global, int first_row, int rows,
+                            int rank, int n_ranks, float density, float accel, float omega,
+                            float free_cells_inv, const void* obstacles_slab, int obstacles_format, int device, int inplace)
+{
+  return create_slab(handle, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
+                     obstacles_slab, obstacles_format, device, inplace != 0);
 }
 
 int lbm_b200_ipc_blob_bytes(void) { return (int)sizeof(IpcBlob); }
@@ -1469,6 +1520,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "staging_bytes")) {
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
     h->opt_staging_bytes = value;
+  } else if (!strcmp(key, "prefetch_rows")) {
+    if (value < 0 || value > 16) return fail(LBM_B200_ERR_ARG, "prefetch_rows must be 0 .. 16");
+    h->opt_prefetch_rows = value;
   } else if (!strcmp(key, "spin_timeout_ms")) {
     if (value < 1 || value > 3600000) return fail(LBM_B200_ERR_ARG, "spin_timeout_ms must be 1 .. 3600000");
     h->opt_spin_timeout_ms = value;
@@ -1505,6 +1559,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
+  else if (!strcmp(key, "prefetch_rows")) *value = h->opt_prefetch_rows;
   else if (!strcmp(key, "spin_timeout_ms")) *value = h->opt_spin_timeout_ms;
   else if (!strcmp(key, "debug_skip_slab")) *value = h->opt_debug_skip_slab;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;

@@ -679,16 +679,13 @@ struct FusedArgs {
   int fold_last;        // whether the launch's last step folds the following step's force in
   int partial_stride;   // doubles between the two steps' partials
   int south_rows, north_rows;   // owned rows of the ring neighbours (PEER)
+  int prefetch_rows;    // L2 prefetch distance in rows (0 = off)
 };
 
 // (destination = a 32-bit shared-window address, converted once per kernel, not per copy)
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gmem)
 {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gmem)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_addr), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -711,11 +708,74 @@ __device__ __forceinline__ void strip_signal(const StepArgs& a, unsigned* flags,
   if (lane == 0) st_release_sys(flags + strip, *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u);
 }
 
-// shared memory of one warp: a three-row ring of the six first-step planes the second step reads later (planes
-// 4,7,8 of a row are consumed straight from registers), one staging row filled by cp.async one row ahead of the
-// arithmetic, and the six end-lane scalars of that row
+// Shared memory of one warp: a three-row ring of the six first-step planes the second step reads later (planes
+// 4,7,8 of a row are consumed straight from registers) and one staging row filled by cp.async one row ahead of the
+// arithmetic.  Every lane reads back only the 16-byte cells it wrote (or copied) itself -- what crosses lanes goes
+// through warp shuffles -- so neither a warp barrier nor an mbarrier sits between the producers and consumers.
 constexpr int kRingPlanes = 6;                                   // ring order: planes 0, 1, 3, 2, 5, 6
-constexpr int kFusedWarpFloat4 = 3 * kRingPlanes * 32 + 9 * 32 + 2;   // + 2 float4 for the end-lane scalars
+constexpr int kRingSlot = kRingPlanes * 32;                      // float4 per ring row
+constexpr int kFusedWarpFloat4 = 3 * kRingSlot + 9 * 32;
+
+// 128-bit accesses that deliver / take two packed pairs in 64-bit registers (no re-packing around the access)
+__device__ __forceinline__ void lds2(const float4* p, f2& a, f2& b)
+{
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+}
+__device__ __forceinline__ void sts2(float4* p, f2 a, f2 b)
+{
+  asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((unsigned)__cvta_generic_to_shared(p)), "l"(a), "l"(b) : "memory");
+}
+template <int HINT>
+__device__ __forceinline__ void stg2(float* p, f2 a, f2 b)
+{
+  if (HINT == 0 || HINT == 3 || HINT == 4) asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+  else asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// The rare path of collide_quad: a row segment with obstacles, or the driven row (the body force folded in).
+__device__ __noinline__ float collide4_generic(float (&f)[4][9], unsigned bits, float omega, bool fold, float aw1, float aw2)
+{
+  float u4 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const bool blocked = (bits >> j) & 1u;
+    const float u = collide(f[j], blocked, omega);
+    u4 = (j == 0) ? u : add(u4, u);
+    if (fold) accelerate(f[j], blocked, aw1, aw2);
+  }
+  return u4;
+}
+
+// A lane's four cells as two packed pairs.  ROT = false: p = cells (0,1), q = cells (2,3); ROT = true: p = cells
+// (1,2), q = cells (3,0).  Which pairing is free of register moves depends on where the operands come from: the
+// six x-shifted populations of a row arrive as an aligned group of four plus one shuffled value, and that value
+// lands in the register its dead neighbour vacated only under ONE of the two pairings (see step1 / step2 below).
+// `any_blocked` and `fold` are warp-uniform.  Returns the lane's sum of |m|/rho in the reference's cell order.
+template <bool ROT>
+__device__ __forceinline__ float collide_quad_fast(f2 (&p)[9], f2 (&q)[9], const StepConst& c)
+{
+  float2 up, uq;
+  collide_pairs(p, q, c.omega, c.negzero, up, uq);
+  return ROT ? add(add(add(uq.y, up.x), up.y), uq.x) : add(add(add(up.x, up.y), uq.x), uq.y);
+}
+template <bool ROT>
+__device__ __forceinline__ float collide_quad_generic(f2 (&p)[9], f2 (&q)[9], unsigned bits, const StepConst& c, bool fold)
+{
+  float f[4][9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const float2 a = unpack2(p[k]), b = unpack2(q[k]);
+    if (ROT) { f[1][k] = a.x; f[2][k] = a.y; f[3][k] = b.x; f[0][k] = b.y; }
+    else { f[0][k] = a.x; f[1][k] = a.y; f[2][k] = b.x; f[3][k] = b.y; }
+  }
+  const float u4 = collide4_generic(f, bits, c.omega, fold, c.aw1, c.aw2);
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    if (ROT) { p[k] = pack2(f[1][k], f[2][k]); q[k] = pack2(f[3][k], f[0][k]); }
+    else { p[k] = pack2(f[0][k], f[1][k]); q[k] = pack2(f[2][k], f[3][k]); }
+  }
+  return u4;
+}
 
 // PEER   = a slab of a multi-GPU ring.  Padded rows: 0 / rows+1 are the halo rows next to the slab, rows+2 / rows+3
 //          the second halo rows (the neighbours' rows one further away); obstacle words of the two adjacent
@@ -725,16 +785,20 @@ constexpr int kFusedWarpFloat4 = 3 * kRingPlanes * 32 + 9 * 32 + 2;   // + 2 flo
 //          0,1,3 + 2,5,6 of its last row and 2,5,6 of the row below go north, 0,1,3 + 4,7,8 of its first row and
 //          4,7,8 of the row above go south -- 9 (+2) plane rows per direction and pair of steps.
 // SINGLE = one timestep only (the odd tail of a run on a ring): the first step's result is the output.
+//
+// Columns: a warp's 32 lanes hold 128 aligned columns, of which lanes 1..30 (120 columns) are the strip's own.  The
+// first step is computed for all 128; its results for the outermost column on either side would need a 129th
+// column and are simply wrong -- nobody reads them: the second step of the own columns needs first-step columns
+// -1 .. 120 of the strip only.  (A shuffle without a source lane returns the lane's own value, so the unused cells
+// stay finite.)
 template <int HINT, bool PEER, bool SINGLE>
 __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const FusedArgs g)
 {
   extern __shared__ float4 fused_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  float4* const ring = fused_smem + (size_t)warp * kFusedWarpFloat4;   // [3][6][32]
-  float4* const stage = ring + 3 * kRingPlanes * 32;                   // [9][32]
-  float* const ends = reinterpret_cast<float*>(stage + 9 * 32);        // [0..2] west (lane 0), [3..5] east (lane 31)
-  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage + lane);   // this lane's cell of staging plane 0
-  const unsigned ends_s = (unsigned)__cvta_generic_to_shared(ends);
+  float4* const ring = fused_smem + (size_t)warp * kFusedWarpFloat4 + lane;   // this lane's cells of [3][6][32]
+  const float4* const stage = ring + 3 * kRingSlot;                           // this lane's cells of [9][32]
+  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
@@ -767,8 +831,6 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       if (gx < 0) gx += nx;
       while (gx >= nx) gx -= nx;
       const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
-      const int xw = (gx == 0) ? nx - 1 : gx - 1;
-      const int xe = (gx + 4 >= nx) ? 0 : gx + 4;
       const uint32_t* const mask_x = a.mask + (gx >> 5);
       const int mask_shift = gx & 31;
 
@@ -780,48 +842,59 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
 
       // ---- asynchronous copy of what the first step of row y pulls, into the staging row; returns the row's
       //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
-      // (q_y = the row the next copy is for; q_s, q_c, q_n = the padded rows it pulls from, rolled forward per copy)
+      // (q_y = the row the next copy is for; q_s, q_c, q_n = the padded rows it pulls from, rolled forward per copy;
+      //  offsets inside a plane are 32-bit: the host refuses slabs of 2^32 cells)
       int q_y = SINGLE ? yb : yb - 1;
       int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
-      auto issue = [&]() -> unsigned {
-        const float* pc = src + (size_t)q_c * nx;
-        const float* ps = src + (size_t)q_s * nx;
-        const float* pn = src + (size_t)q_n * nx;
-        cp_async16(stage_s + 0 * 512, pc + 0 * P + gx);
-        cp_async16(stage_s + 1 * 512, pc + 1 * P + gx);
-        cp_async16(stage_s + 2 * 512, ps + 2 * P + gx);
-        cp_async16(stage_s + 3 * 512, pc + 3 * P + gx);
-        cp_async16(stage_s + 4 * 512, pn + 4 * P + gx);
-        cp_async16(stage_s + 5 * 512, ps + 5 * P + gx);
-        cp_async16(stage_s + 6 * 512, ps + 6 * P + gx);
-        cp_async16(stage_s + 7 * 512, pn + 7 * P + gx);
-        cp_async16(stage_s + 8 * 512, pn + 8 * P + gx);
-        if (lane == 0) {
-          cp_async4(ends_s + 0, pc + 1 * P + xw);
-          cp_async4(ends_s + 4, ps + 5 * P + xw);
-          cp_async4(ends_s + 8, pn + 8 * P + xw);
-        } else if (lane == 31) {
-          cp_async4(ends_s + 12, pc + 3 * P + xe);
-          cp_async4(ends_s + 16, ps + 6 * P + xe);
-          cp_async4(ends_s + 20, pn + 7 * P + xe);
+      // L2 prefetch kPrefetchRows rows ahead of the copy: lane k < 9 asks for plane k's 512-byte row piece with one
+      // bulk-prefetch instruction, so that the copy into shared memory finds its data in L2 (with the copy only one
+      // row ahead of the arithmetic, 19 % of all stall samples sat on the first read of the staging row).
+      // Every (row, plane) piece of the band is requested once: plane k is pulled from row y + pf_dy of the row y
+      // it is used for.
+      const int pf_dy = (lane == 0 || lane == 1 || lane == 3) ? 0 : ((lane == 2 || lane == 5 || lane == 6) ? -1 : 1);
+      int pf_x = strip * kStripOut - 4;                       // a contiguous piece even where the strip wraps around
+      pf_x = max(0, min(pf_x, nx - 128));
+      const float* const pf_base = src + (size_t)min(lane, 8) * P + pf_x;
+      const int pf_last = SINGLE ? ye - 1 : ye;               // last row whose first step this item computes
+      auto prefetch_row = [&](const int y) {                  // what the first step of row y pulls
+        if (lane < 9 && y <= pf_last) {
+          const float* p = pf_base + (unsigned)prow(y + pf_dy) * (unsigned)nx;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(512u) : "memory");
         }
+      };
+      for (int d = 1; d < g.prefetch_rows; d++) prefetch_row(q_y + d);
+      auto issue = [&]() -> unsigned {
+        if (g.prefetch_rows > 0) prefetch_row(q_y + g.prefetch_rows);
+        const float* pc = src + ((unsigned)q_c * (unsigned)nx + (unsigned)gx);
+        const float* ps = src + ((unsigned)q_s * (unsigned)nx + (unsigned)gx);
+        const float* pn = src + ((unsigned)q_n * (unsigned)nx + (unsigned)gx);
+        cp_async16(stage_s + 0 * 512, pc + 0 * P);
+        cp_async16(stage_s + 1 * 512, pc + 1 * P);
+        cp_async16(stage_s + 2 * 512, ps + 2 * P);
+        cp_async16(stage_s + 3 * 512, pc + 3 * P);
+        cp_async16(stage_s + 4 * 512, pn + 4 * P);
+        cp_async16(stage_s + 5 * 512, ps + 5 * P);
+        cp_async16(stage_s + 6 * 512, ps + 6 * P);
+        cp_async16(stage_s + 7 * 512, pn + 7 * P);
+        cp_async16(stage_s + 8 * 512, pn + 8 * P);
         cp_async_commit();
         // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
         const int mrow = EDGE ? ((q_y < 0) ? rows : (q_y >= rows ? rows + 1 : q_y)) : q_c - 1;
-        const unsigned word = __ldg(mask_x + (size_t)mrow * a.mask_row_words);   // used a whole row later: no stall here
+        const unsigned word = __ldg(mask_x + (unsigned)mrow * (unsigned)a.mask_row_words);   // used a whole row later: no stall here
         q_y++;
         q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
         return word;
       };
 
-      // ---- a finished (owned) row y: to the destination buffer and, on a ring, into the neighbours' halo rows ----
-      auto emit = [&](const int y, float (&f)[4][9]) {
-        const size_t o = (size_t)(y + 1) * nx + gx;
+      // ---- a finished (owned) row y (o[k] = plane k of the lane's four columns): to the destination buffer and, on
+      //      a ring, into the neighbours' halo rows ----
+      auto emit = [&](const int y, const f2 (&p)[9], const f2 (&q)[9]) {
+        float* const d = dst + ((unsigned)(y + 1) * (unsigned)nx + (unsigned)gx);
 #pragma unroll
-        for (int k = 0; k < 9; k++) store4<HINT>(dst + k * P + o, make_float4(f[0][k], f[1][k], f[2][k], f[3][k]));
+        for (int k = 0; k < 9; k++) stg2<HINT>(d + k * P, p[k], q[k]);
         if (EDGE && (y <= 1 || y >= rows - 2)) {
           auto put = [&](float* base, size_t plane, int row, int k) {
-            *reinterpret_cast<float4*>(base + k * plane + (size_t)row * nx + gx) = make_float4(f[0][k], f[1][k], f[2][k], f[3][k]);
+            stg2<0>(base + k * plane + (size_t)row * nx + gx, p[k], q[k]);
           };
           if (y == 0) {                                        // the southern slab's halo row rows+1
             const int r = g.south_rows + 1;
@@ -851,115 +924,128 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         }
       };
 
-      // ---- first step of row y out of the staging row (mword = its obstacle word); the six planes the second step
-      //      needs later go into ring slot `slot`, planes 4,7,8 come back in registers.  With `ahead` the copy for
-      //      row y+1 is issued as soon as the staging row has been read; its obstacle word is returned. ----
-      auto step1 = [&](const int y, const unsigned mword, const int slot, const bool ahead, float4& k4, float4& k7, float4& k8) -> unsigned {
+      // ---- first step of row y out of the staging row (mword = its obstacle word).  The lane's four cells run as
+      //      the pairs (1,2) and (3,0): a west-moving population's cells 1,2 are the first half of its aligned group
+      //      and cell 3 + the value shuffled in for cell 0 fill the second half (mirrored for east-moving ones), so
+      //      only the three unshifted planes need register moves.  Results keep that rotated order (columns 1,2,3,0
+      //      of the group): six planes go into ring row `slot`, planes 4,7,8 come back in registers.  With `ahead`
+      //      the copy for row y+1 is issued as soon as the staging row has been read; its obstacle word is returned.
+      auto step1 = [&](const int y, const unsigned mword, float4* const slot, const bool ahead, const bool count,
+                       f2 (&kp)[3], f2 (&kq)[3]) -> unsigned {
         cp_async_wait_all();
-        float4 c[9];
+        f2 lo[9], hi[9];                                         // lo = columns 0,1 of the lane's group, hi = columns 2,3
 #pragma unroll
-        for (int k = 0; k < 9; k++) c[k] = stage[k * 32 + lane];
-        const bool we = (lane == 0), ee = (lane == 31);
-        float e_c = 0.f, e_s = 0.f, e_n = 0.f;
-        if (we || ee) { e_c = ends[we ? 0 : 3]; e_s = ends[we ? 1 : 4]; e_n = ends[we ? 2 : 5]; }
-        const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
-        const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
-        const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
-        const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
-        const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
-        const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-        float f[4][9];
-        f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
-        f[0][1] = we ? e_c : up1; f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
-        f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
-        f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = ee ? e_c : dn3;
-        f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
-        f[0][5] = we ? e_s : up5; f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
-        f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = ee ? e_s : dn6;
-        f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = ee ? e_n : dn7;
-        f[0][8] = we ? e_n : up8; f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
+        for (int k = 0; k < 9; k++) lds2(stage + k * 32, lo[k], hi[k]);
+        const float up1 = __shfl_up_sync(0xffffffffu, hi2(hi[1]), 1);
+        const float up5 = __shfl_up_sync(0xffffffffu, hi2(hi[5]), 1);
+        const float up8 = __shfl_up_sync(0xffffffffu, hi2(hi[8]), 1);
+        const float dn3 = __shfl_down_sync(0xffffffffu, lo2(lo[3]), 1);
+        const float dn6 = __shfl_down_sync(0xffffffffu, lo2(lo[6]), 1);
+        const float dn7 = __shfl_down_sync(0xffffffffu, lo2(lo[7]), 1);
         // every lane has read its own staging cells (the shuffles consumed them): the next row's copy may start and
         // flies during both steps' arithmetic
         const unsigned word_next = ahead ? issue() : 0u;
-        const unsigned bits = mword >> mask_shift;
+        f2 p[9], q[9];                                         // p = cells (1,2), q = cells (3,0)
+        p[0] = pack2(hi2(lo[0]), lo2(hi[0])); q[0] = pack2(hi2(hi[0]), lo2(lo[0]));
+        p[2] = pack2(hi2(lo[2]), lo2(hi[2])); q[2] = pack2(hi2(hi[2]), lo2(lo[2]));
+        p[4] = pack2(hi2(lo[4]), lo2(hi[4])); q[4] = pack2(hi2(hi[4]), lo2(lo[4]));
+        p[1] = lo[1]; q[1] = pack2(lo2(hi[1]), up1);
+        p[5] = lo[5]; q[5] = pack2(lo2(hi[5]), up5);
+        p[8] = lo[8]; q[8] = pack2(lo2(hi[8]), up8);
+        p[3] = hi[3]; q[3] = pack2(dn3, hi2(lo[3]));
+        p[6] = hi[6]; q[6] = pack2(dn6, hi2(lo[6]));
+        p[7] = hi[7]; q[7] = pack2(dn7, hi2(lo[7]));
+        const unsigned bits = (mword >> mask_shift) & 0xFu;
         const bool fold = (SINGLE ? g.fold_last != 0 : true) && (y + 1 == g.accel_row);   // the driven row is an owned row
-        const bool any_blocked = __any_sync(0xffffffffu, (bits & 0xFu) != 0u);
-        const float u4 = collide4(f, bits, any_blocked, a.c, fold);
-        if (owned && y >= yb && y < ye) acc1 += (double)u4;
-        if (SINGLE) {
-          if (owned) emit(y, f);
-          publish(y);
-          return word_next;
-        }
-        __syncwarp();                                          // the slot's previous readers are done
-        float4* out = ring + slot * (kRingPlanes * 32) + lane;
-        out[0 * 32] = make_float4(f[0][0], f[1][0], f[2][0], f[3][0]);
-        out[1 * 32] = make_float4(f[0][1], f[1][1], f[2][1], f[3][1]);
-        out[2 * 32] = make_float4(f[0][3], f[1][3], f[2][3], f[3][3]);
-        out[3 * 32] = make_float4(f[0][2], f[1][2], f[2][2], f[3][2]);
-        out[4 * 32] = make_float4(f[0][5], f[1][5], f[2][5], f[3][5]);
-        out[5 * 32] = make_float4(f[0][6], f[1][6], f[2][6], f[3][6]);
-        k4 = make_float4(f[0][4], f[1][4], f[2][4], f[3][4]);
-        k7 = make_float4(f[0][7], f[1][7], f[2][7], f[3][7]);
-        k8 = make_float4(f[0][8], f[1][8], f[2][8], f[3][8]);
+        const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
+        // (each branch stores its own results: a join would pin 36 registers to common locations)
+        auto finish = [&](const float u4) {
+          acc1 += (double)(count ? u4 : 0.0f);
+          if (SINGLE) {
+            if (owned) {
+              f2 op[9], oq[9];                                 // back to column order: cells (0,1), (2,3)
+#pragma unroll
+              for (int k = 0; k < 9; k++) { op[k] = pack2(hi2(q[k]), lo2(p[k])); oq[k] = pack2(hi2(p[k]), lo2(q[k])); }
+              emit(y, op, oq);
+            }
+            return;
+          }
+          sts2(slot + 0 * 32, p[0], q[0]);
+          sts2(slot + 1 * 32, p[1], q[1]);
+          sts2(slot + 2 * 32, p[3], q[3]);
+          sts2(slot + 3 * 32, p[2], q[2]);
+          sts2(slot + 4 * 32, p[5], q[5]);
+          sts2(slot + 5 * 32, p[6], q[6]);
+          kp[0] = p[4]; kq[0] = q[4]; kp[1] = p[7]; kq[1] = q[7]; kp[2] = p[8]; kq[2] = q[8];
+        };
+        if (!any_blocked && !fold) finish(collide_quad_fast<true>(p, q, a.c));
+        else finish(collide_quad_generic<true>(p, q, bits, a.c, fold));
+        if (SINGLE) publish(y);
         return word_next;
       };
 
-      // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (slot s_s), planes 0,1,3 of
-      //      row y (slot s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran ----
-      auto step2 = [&](const int y, const unsigned mword, const int s_s, const int s_c, const float4 k4, const float4 k7, const float4 k8) {
-        const int row = y + 1;
-        __syncwarp();                                          // ring rows are complete
-        const float4* rs_ = ring + s_s * (kRingPlanes * 32) + lane;
-        const float4* rc_ = ring + s_c * (kRingPlanes * 32) + lane;
-        float4 c[9];
-        c[0] = rc_[0 * 32]; c[1] = rc_[1 * 32]; c[3] = rc_[2 * 32];
-        c[2] = rs_[3 * 32]; c[5] = rs_[4 * 32]; c[6] = rs_[5 * 32];
-        c[4] = k4; c[7] = k7; c[8] = k8;
-        const float up1 = __shfl_up_sync(0xffffffffu, c[1].w, 1);
-        const float up5 = __shfl_up_sync(0xffffffffu, c[5].w, 1);
-        const float up8 = __shfl_up_sync(0xffffffffu, c[8].w, 1);
-        const float dn3 = __shfl_down_sync(0xffffffffu, c[3].x, 1);
-        const float dn6 = __shfl_down_sync(0xffffffffu, c[6].x, 1);
-        const float dn7 = __shfl_down_sync(0xffffffffu, c[7].x, 1);
-        const bool any_blocked = __any_sync(0xffffffffu, ((mword >> mask_shift) & 0xFu) != 0u);
+      // ---- second step of row y (0-based, owned): planes 2,5,6 of first-step row y-1 (ring row s_s), planes 0,1,3
+      //      of row y (ring row s_c), planes 4,7,8 of row y+1 from the registers of the first step that just ran.
+      //      All of them hold columns 1,2,3,0 of the lane's group; here the cells run as the pairs (0,1) and (2,3),
+      //      which again leaves only the unshifted planes with register moves and yields the output in column order.
+      auto step2 = [&](const int y, const unsigned mword, const float4* const s_s, const float4* const s_c,
+                       const f2 (&kp)[3], const f2 (&kq)[3]) {
+        f2 lo[9], hi[9];                                         // lo = columns 1,2 of the lane's group, hi = columns 3,0
+        lds2(s_c + 0 * 32, lo[0], hi[0]); lds2(s_c + 1 * 32, lo[1], hi[1]); lds2(s_c + 2 * 32, lo[3], hi[3]);
+        lds2(s_s + 3 * 32, lo[2], hi[2]); lds2(s_s + 4 * 32, lo[5], hi[5]); lds2(s_s + 5 * 32, lo[6], hi[6]);
+        lo[4] = kp[0]; hi[4] = kq[0]; lo[7] = kp[1]; hi[7] = kq[1]; lo[8] = kp[2]; hi[8] = kq[2];
+        // cell 0 of an east-moving population comes from the previous lane's column 3, cell 3 of a west-moving one
+        // from the next lane's column 0
+        const float up1 = __shfl_up_sync(0xffffffffu, lo2(hi[1]), 1);
+        const float up5 = __shfl_up_sync(0xffffffffu, lo2(hi[5]), 1);
+        const float up8 = __shfl_up_sync(0xffffffffu, lo2(hi[8]), 1);
+        const float dn3 = __shfl_down_sync(0xffffffffu, hi2(hi[3]), 1);
+        const float dn6 = __shfl_down_sync(0xffffffffu, hi2(hi[6]), 1);
+        const float dn7 = __shfl_down_sync(0xffffffffu, hi2(hi[7]), 1);
+        const unsigned bits = (mword >> mask_shift) & 0xFu;
+        const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
         if (!owned) return;
-        float f[4][9];
-        f[0][0] = c[0].x; f[1][0] = c[0].y; f[2][0] = c[0].z; f[3][0] = c[0].w;
-        f[0][1] = up1;    f[1][1] = c[1].x; f[2][1] = c[1].y; f[3][1] = c[1].z;
-        f[0][2] = c[2].x; f[1][2] = c[2].y; f[2][2] = c[2].z; f[3][2] = c[2].w;
-        f[0][3] = c[3].y; f[1][3] = c[3].z; f[2][3] = c[3].w; f[3][3] = dn3;
-        f[0][4] = c[4].x; f[1][4] = c[4].y; f[2][4] = c[4].z; f[3][4] = c[4].w;
-        f[0][5] = up5;    f[1][5] = c[5].x; f[2][5] = c[5].y; f[3][5] = c[5].z;
-        f[0][6] = c[6].y; f[1][6] = c[6].z; f[2][6] = c[6].w; f[3][6] = dn6;
-        f[0][7] = c[7].y; f[1][7] = c[7].z; f[2][7] = c[7].w; f[3][7] = dn7;
-        f[0][8] = up8;    f[1][8] = c[8].x; f[2][8] = c[8].y; f[3][8] = c[8].z;
-        const unsigned bits = mword >> mask_shift;
-        const bool fold = g.fold_last && (row == g.accel_row);
-        const float u4 = collide4(f, bits, any_blocked, a.c, fold);
-        acc2 += (double)u4;
-        emit(y, f);
+        f2 p[9], q[9];                                         // p = cells (0,1), q = cells (2,3)
+        p[0] = pack2(hi2(hi[0]), lo2(lo[0])); q[0] = pack2(hi2(lo[0]), lo2(hi[0]));
+        p[2] = pack2(hi2(hi[2]), lo2(lo[2])); q[2] = pack2(hi2(lo[2]), lo2(hi[2]));
+        p[4] = pack2(hi2(hi[4]), lo2(lo[4])); q[4] = pack2(hi2(lo[4]), lo2(hi[4]));
+        p[1] = pack2(up1, hi2(hi[1])); q[1] = lo[1];
+        p[5] = pack2(up5, hi2(hi[5])); q[5] = lo[5];
+        p[8] = pack2(up8, hi2(hi[8])); q[8] = lo[8];
+        p[3] = lo[3]; q[3] = pack2(lo2(hi[3]), dn3);
+        p[6] = lo[6]; q[6] = pack2(lo2(hi[6]), dn6);
+        p[7] = lo[7]; q[7] = pack2(lo2(hi[7]), dn7);
+        const bool fold = g.fold_last && (y + 1 == g.accel_row);
+        if (!any_blocked && !fold) {
+          acc2 += (double)collide_quad_fast<false>(p, q, a.c);
+          emit(y, p, q);
+        } else {
+          acc2 += (double)collide_quad_generic<false>(p, q, bits, a.c, fold);
+          emit(y, p, q);
+        }
       };
 
-      float4 k4, k7, k8;
+      f2 kp[3], kq[3];
       if (SINGLE) {
         unsigned word = issue();
-        for (int y = yb; y < ye; y++) word = step1(y, word, 0, y + 1 < ye, k4, k7, k8);
+#pragma unroll 1
+        for (int y = yb; y < ye; y++) word = step1(y, word, ring, y + 1 < ye, owned, kp, kq);
       } else {
-        // rows yb-1 and yb first; then every owned row: first step of the row above, second step of the row itself
-        const unsigned word_s = issue();
-        unsigned word_c = step1(yb - 1, word_s, 0, true, k4, k7, k8);        // -> word of row yb
-        unsigned word_n = step1(yb, word_c, 1, true, k4, k7, k8);            // -> word of row yb+1
-        int s_s = 0, s_c = 1, s_n = 2;
-        for (int y = yb; y < ye; y++) {
-          const unsigned word_nn = step1(y + 1, word_n, s_n, y + 1 < ye, k4, k7, k8);
-          step2(y, word_c, s_s, s_c, k4, k7, k8);
-          publish(y);
-          word_c = word_n; word_n = word_nn;
-          const int t = s_s; s_s = s_c; s_c = s_n; s_n = t;
+        // rows yb-1 .. ye get their first step; every owned row gets its second step as soon as the first step of
+        // the row above it has run.  (w_c, w_n = obstacle words of the rows the next second / first step is for.)
+        unsigned w_c = 0u, w_n = issue();
+        float4 *s_s = ring, *s_c = ring + kRingSlot, *s_n = ring + 2 * kRingSlot;
+#pragma unroll 1
+        for (int r = yb - 1; r <= ye; r++) {
+          const unsigned w_nn = step1(r, w_n, s_n, r < ye, owned && r >= yb && r < ye, kp, kq);
+          if (r > yb) {
+            step2(r - 1, w_c, s_s, s_c, kp, kq);
+            publish(r - 1);
+          }
+          w_c = w_n; w_n = w_nn;
+          float4* const t = s_s; s_s = s_c; s_c = s_n; s_n = t;
         }
       }
-      __syncwarp();
     };
     if (PEER && (band == 0 || band == g.bands - 1)) run_item(std::true_type{});
     else run_item(std::false_type{});
@@ -1162,6 +1248,48 @@ __global__ void pack_mask(const int* obstacles, int nx, int rows, int row_words,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if (lane == 0 && n && blocked_cells) atomicAdd(blocked_cells, (unsigned long long)n);
+}
+
+// The same from one byte per cell (LBM_B200_OBST_UINT8): a quarter of the upload.
+__global__ void pack_mask_u8(const unsigned char* obstacles, int nx, int rows, int row_words, uint32_t* mask,
+                             unsigned long long* blocked_cells)
+{
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int groups = (row_words + 31) / 32;
+  if (warp >= (long)rows * groups) return;
+  const int r = (int)(warp / groups);
+  const int w0 = (int)(warp - (long)r * groups) * 32;
+  const unsigned char* row = obstacles + (size_t)r * nx;
+  uint32_t mine = 0;
+  for (int i = 0; i < 32; i++) {
+    const int x = (w0 + i) * 32 + lane;
+    const unsigned word = __ballot_sync(0xffffffffu, x < nx && row[x] != 0);
+    if (i == lane) mine = word;
+  }
+  if (w0 + lane < row_words) mask[(size_t)r * row_words + w0 + lane] = mine;
+  unsigned n = __popc(mine);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0 && n && blocked_cells) atomicAdd(blocked_cells, (unsigned long long)n);
+}
+
+// Already bit-packed rows (LBM_B200_OBST_BITS, the device layout): clear the padding bits past nx in the last word
+// of every row and count the blocked cells.
+__global__ void adopt_mask_bits(uint32_t* mask, int nx, int rows, int row_words, unsigned long long* blocked_cells)
+{
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned n = 0;
+  if (i < (long)rows * row_words) {
+    const int w = (int)(i % row_words);
+    uint32_t v = mask[i];
+    const int valid = nx - w * 32;                            // cells this word covers
+    if (valid < 32) { v &= (1u << valid) - 1u; mask[i] = v; }
+    n = __popc(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n && blocked_cells) atomicAdd(blocked_cells, (unsigned long long)n);
 }
 
 // uniform initial state, every padded row (d2q9-bgk.c:880-902)

@@ -28,6 +28,33 @@ def _ip(a: np.ndarray):
     return a.ctypes.data_as(c_int_p)
 
 
+OBSTACLE_FORMATS = {"int32": 0, "uint8": 1, "bits": 2}      # LBM_B200_OBST_* of include/lbm_b200.h
+
+
+def _obstacle_buffer(obstacles, rows: int, nx: int, fmt: str) -> np.ndarray:
+    """The caller's obstacle rows as the contiguous host array the C-ABI expects for `fmt`."""
+    if fmt not in OBSTACLE_FORMATS:
+        raise ValueError(f"obstacles_format must be one of {sorted(OBSTACLE_FORMATS)}")
+    if fmt == "bits":
+        ob = np.ascontiguousarray(obstacles)
+        if ob.dtype not in (np.uint32, np.int32) or ob.shape != (rows, (nx + 31) // 32):
+            raise ValueError(f"bit-packed obstacles must be (u)int32 of shape ({rows}, {(nx + 31) // 32}), got {ob.dtype} {ob.shape}")
+        return ob
+    ob = np.ascontiguousarray(obstacles, np.int32 if fmt == "int32" else np.uint8)
+    if ob.shape != (rows, nx):
+        raise ValueError(f"obstacles must have shape ({rows}, {nx}), got {ob.shape}")
+    return ob
+
+
+def pack_obstacle_bits(obstacles: np.ndarray) -> np.ndarray:
+    """[rows, nx] (non-zero = blocked) -> the "bits" format: uint32 [rows, ceil(nx / 32)], cell x = bit x & 31 of word x >> 5."""
+    rows, nx = obstacles.shape
+    words = (nx + 31) // 32
+    padded = np.zeros((rows, words * 32), np.uint8)
+    padded[:, :nx] = np.asarray(obstacles) != 0
+    return np.ascontiguousarray(np.packbits(padded, axis=1, bitorder="little")).view(np.uint32).reshape(rows, words)
+
+
 def decompose(ny: int, n_slabs: int):
     """Rows and first row of every slab (reference d2q9-bgk.c:834-862). Host only."""
     rows = np.zeros(n_slabs, np.int32)
@@ -55,12 +82,10 @@ class Simulation:
     """
 
     def __init__(self, nx, ny, density, accel, omega, obstacles, n_slabs: int = 1, devices=None, device=None,
-                 inplace: bool = False):
+                 inplace: bool = False, obstacles_format: str = "int32"):
         self._h = handle_t()
         self._lib = library()
-        ob = np.ascontiguousarray(obstacles, np.int32)
-        if ob.shape != (ny, nx):
-            raise ValueError(f"obstacles must have shape ({ny}, {nx}), got {ob.shape}")
+        ob = _obstacle_buffer(obstacles, ny, nx, obstacles_format)
         if device is not None and devices is None:
             devices = [device] * n_slabs
         dev = None
@@ -68,24 +93,32 @@ class Simulation:
             dev = np.ascontiguousarray(devices, np.int32)
             if dev.shape != (n_slabs,):
                 raise ValueError("devices must list one device per slab")
-        create = self._lib.lbm_b200_create_inplace if inplace else self._lib.lbm_b200_create
-        _check(create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
-                      _ip(dev) if dev is not None else None))
+        if obstacles_format == "int32":                      # the reference's layout: the plain entry points
+            create = self._lib.lbm_b200_create_inplace if inplace else self._lib.lbm_b200_create
+            _check(create(ctypes.byref(self._h), nx, ny, density, accel, omega, _ip(ob), n_slabs,
+                          _ip(dev) if dev is not None else None))
+        else:
+            _check(self._lib.lbm_b200_create_ex(ctypes.byref(self._h), nx, ny, density, accel, omega, ob.ctypes.data,
+                                                OBSTACLE_FORMATS[obstacles_format], n_slabs,
+                                                _ip(dev) if dev is not None else None, 1 if inplace else 0))
         self.nx, self.ny = nx, ny
         self._set_shape()
 
     @classmethod
     def slab(cls, nx, ny_global, first_row, rows, rank, n_ranks, density, accel, omega, free_cells_inv,
-             obstacles_slab, device, inplace: bool = False):
+             obstacles_slab, device, inplace: bool = False, obstacles_format: str = "int32"):
         self = cls.__new__(cls)
         self._h = handle_t()
         self._lib = library()
-        ob = np.ascontiguousarray(obstacles_slab, np.int32)
-        if ob.shape != (rows, nx):
-            raise ValueError(f"obstacles_slab must have shape ({rows}, {nx}), got {ob.shape}")
-        create = self._lib.lbm_b200_create_slab_inplace if inplace else self._lib.lbm_b200_create_slab
-        _check(create(ctypes.byref(self._h), nx, ny_global, first_row, rows, rank, n_ranks,
-                      density, accel, omega, free_cells_inv, _ip(ob), device))
+        ob = _obstacle_buffer(obstacles_slab, rows, nx, obstacles_format)
+        if obstacles_format == "int32":
+            create = self._lib.lbm_b200_create_slab_inplace if inplace else self._lib.lbm_b200_create_slab
+            _check(create(ctypes.byref(self._h), nx, ny_global, first_row, rows, rank, n_ranks,
+                          density, accel, omega, free_cells_inv, _ip(ob), device))
+        else:
+            _check(self._lib.lbm_b200_create_slab_ex(ctypes.byref(self._h), nx, ny_global, first_row, rows, rank, n_ranks,
+                                                     density, accel, omega, free_cells_inv, ob.ctypes.data,
+                                                     OBSTACLE_FORMATS[obstacles_format], device, 1 if inplace else 0))
         self.nx, self.ny = nx, ny_global
         self._set_shape()
         return self
