@@ -66,6 +66,13 @@ const char* lbm_b200_last_error(void);
 /* Number of visible CUDA devices (0 if there is none or the driver is missing). */
 int lbm_b200_device_count(void);
 
+/* Device self-test of the arithmetic restatements the step kernels rely on for bit-identity with the reference
+ * (csrc/lbm_cell.cuh): counts[0] / counts[1] = floats in [2^-101, 2^126) whose restated reciprocal / square root
+ * differs from CUDA's correctly rounded __frcp_rn / __fsqrt_rn (all 1.9e9 bit patterns are tried), counts[2] =
+ * packed fp32x2 add / sub / mul results that differ from the scalar IEEE operations over 2^28 operand pairs drawn
+ * from all bit patterns.  All three must be 0.  No counterpart in the reference. */
+int lbm_b200_selftest(int device, unsigned long long counts[3]);
+
 /* ---- whole-domain solver in one process -------------------------------------------- */
 
 /* Replaces the device-independent part of initialise() (d2q9-bgk.c:865-902, 966-970):

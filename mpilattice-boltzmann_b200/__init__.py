@@ -6,4 +6,4 @@ The product is the C-ABI library (include/lbm_b200.h, csrc/) and the C host prog
 from . import decks, parity  # noqa: F401
 from ._lib import EXE_PATH, LIB_PATH, SIGNATURES, library  # noqa: F401
 from .solver import (LBMError, Simulation, decompose, device_count, free_cells_inv,  # noqa: F401
-                     pack_obstacle_bits)
+                     pack_obstacle_bits, selftest)

@@ -42,6 +42,7 @@ SIGNATURES = {
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int]),
+    "lbm_b200_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lbm_b200_ipc_blob_bytes": (ctypes.c_int, []),
     "lbm_b200_ipc_export": (ctypes.c_int, [handle_t, ctypes.c_void_p]),
     "lbm_b200_ipc_connect": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_void_p]),

@@ -72,6 +72,7 @@ struct Slab {
   size_t bounce_bytes = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;   // device-to-host copies of get_final_state, overlapped with its kernels
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   Neighbour south, north;
   int accel_row = -1;                   // padded row of global row ny-2, or -1 if another slab owns it
@@ -122,7 +123,7 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
-  long opt_prefetch_rows = 3;           // kernel 5: L2 prefetch distance in rows
+  long opt_prefetch_rows = 0;           // kernel 5: L2 prefetch distance in rows (0 = off: measured slower, profiles/r02_fused2.md)
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
   long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
   bool failed = false;                  // a wait timed out: the state is garbage, only destroy is valid
@@ -845,6 +846,26 @@ int lbm_b200_device_count(void)
   return n;
 }
 
+int lbm_b200_selftest(int device, unsigned long long counts[3])
+{
+  if (!counts) return fail(LBM_B200_ERR_ARG, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(LBM_B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(LBM_B200_ERR_ARG, "device %d requested but %d device(s) are visible", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  unsigned long long* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, 3 * sizeof(unsigned long long)));
+  cudaError_t e = cudaMemset(dev, 0, 3 * sizeof(unsigned long long));
+  if (e == cudaSuccess) {
+    lbm::selftest_math<<<148 * 16, 256>>>(dev, 1ull << 28, -0.0f);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(counts, dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) return fail(LBM_B200_ERR_CUDA, "self-test failed to run: %s", cudaGetErrorString(e));
+  return LBM_B200_OK;
+}
+
 int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row)
 {
   if (ny < 1 || n_slabs < 1 || !rows || !first_row) return fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_decompose");
@@ -1474,6 +1495,41 @@ int lbm_b200_get_final_state(lbm_b200* h, float* u_x, float* u_y, float* u, floa
     int step = 0;
     int rc = staging(h, s, (size_t)h->nx * 4 * sizeof(float), s.rows, &scratch, &step);
     if (rc) return rc;
+    if (step >= s.rows && s.rows >= 64) {
+      // The scratch holds the whole slab (ping-pong handles: the idle buffer): cut it into row chunks and let the
+      // epilogue kernel of chunk c+1 run while chunk c is on its way to the host -- kernels on the slab's stream,
+      // copies on a second stream, one event per chunk.  (The reference computes these fields on the host while it
+      // prints them, d2q9-bgk.c:1076-1111.)
+      constexpr int kChunks = 8;
+      if (!s.copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+      cudaEvent_t ev[kChunks] = {};
+      const int rows_per = (s.rows + kChunks - 1) / kChunks;
+      cudaError_t e = cudaSuccess;
+      size_t off = 0;                                 // cells of the slab done so far
+      for (int c = 0; c < kChunks && e == cudaSuccess; c++) {
+        const int r0 = c * rows_per, n = std::min(rows_per, s.rows - r0);
+        if (n <= 0) break;
+        const size_t ncell = (size_t)n * h->nx;
+        float* part = scratch + 4 * off;
+        lbm::final_state<<<(unsigned)((ncell + 255) / 256), 256, 0, s.stream>>>(s.buf[h->inplace ? 0 : h->cur], layout_of(h, s), 1 + r0,
+                                                                                s.mask, h->mask_row_words, ncell, h->density, part);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[c], s.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s.copy_stream, ev[c], 0);
+        for (int k = 0; k < 4 && e == cudaSuccess; k++)
+          if (outs[k]) e = cudaMemcpyAsync(outs[k] + done + off, part + (size_t)k * ncell, ncell * sizeof(float), cudaMemcpyDeviceToHost, s.copy_stream);
+        off += ncell;
+      }
+      cudaError_t e2 = cudaStreamSynchronize(s.copy_stream);
+      cudaError_t e3 = cudaStreamSynchronize(s.stream);
+      for (cudaEvent_t x : ev)
+        if (x) cudaEventDestroy(x);
+      if (e == cudaSuccess) e = (e2 != cudaSuccess) ? e2 : e3;
+      if (e != cudaSuccess) return fail(LBM_B200_ERR_CUDA, "reading back the macroscopic fields failed: %s", cudaGetErrorString(e));
+      done += (size_t)s.rows * h->nx;
+      continue;
+    }
     for (int r = 0; r < s.rows; r += step) {
       const size_t ncell = (size_t)std::min(step, s.rows - r) * h->nx;
       const unsigned blocks = (unsigned)((ncell + 255) / 256);
@@ -1598,6 +1654,7 @@ void lbm_b200_destroy(lbm_b200* h)
     if (s.cursor) cudaFree(s.cursor);
     if (s.blocked_dev) cudaFree(s.blocked_dev);
     if (s.bounce) cudaFree(s.bounce);
+    if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
   }

@@ -1292,6 +1292,52 @@ __global__ void adopt_mask_bits(uint32_t* mask, int nx, int rows, int row_words,
   if ((threadIdx.x & 31) == 0 && n && blocked_cells) atomicAdd(blocked_cells, (unsigned long long)n);
 }
 
+// ---------------------------------------------------------------------------------------
+// Self-test of the arithmetic restatements (lbm_b200_selftest): counts[0] = floats in the fast range whose rcp_fast
+// differs from __frcp_rn, counts[1] = the same for sqrt_fast / __fsqrt_rn (every bit pattern in [kFastLo, kFastHi] is
+// tried), counts[2] = packed add/sub/mul results that differ from the scalar intrinsics over `pairs` pseudo-random
+// operand pairs drawn from ALL bit patterns (NaN results compare equal to NaN results).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool same_float(float a, float b)
+{
+  return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+}
+__global__ void selftest_math(unsigned long long* counts, unsigned long long pairs, float nz)
+{
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned bad_rcp = 0, bad_sqrt = 0, bad_packed = 0;
+  for (unsigned long long b = kFastLo + tid; b <= kFastHi; b += nthreads) {
+    const float x = __uint_as_float((unsigned)b);
+    if (__float_as_uint(rcp_fast(x)) != __float_as_uint(__frcp_rn(x))) bad_rcp++;
+    if (__float_as_uint(sqrt_fast(x)) != __float_as_uint(__fsqrt_rn(x))) bad_sqrt++;
+  }
+  for (unsigned long long i = tid; i < pairs; i += nthreads) {
+    // four 32-bit patterns from a counter hash (splitmix64); every exponent, both signs, NaNs and infinities occur
+    unsigned long long z = i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull, w[2];
+    for (int j = 0; j < 2; j++) {
+      z += 0x9E3779B97F4A7C15ull;
+      unsigned long long t = z;
+      t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull;
+      t = (t ^ (t >> 27)) * 0x94D049BB133111EBull;
+      w[j] = t ^ (t >> 31);
+    }
+    const float a0 = __uint_as_float((unsigned)w[0]), a1 = __uint_as_float((unsigned)(w[0] >> 32));
+    const float b0 = __uint_as_float((unsigned)w[1]), b1 = __uint_as_float((unsigned)(w[1] >> 32));
+    const f2 a = pack2(a0, a1), b = pack2(b0, b1);
+    const float2 s = unpack2(add2(a, b)), d = unpack2(sub2(a, b)), m = unpack2(mul2(a, b, nz)), ms = unpack2(mul2(a, b0, nz));
+    // (the multiply followed by an add: the pattern ptxas would contract into one FFMA2 if it saw a plain product)
+    const float2 ma = unpack2(add2(mul2(a, b, nz), a));
+    bad_packed += !same_float(s.x, add(a0, b0)) + !same_float(s.y, add(a1, b1)) + !same_float(d.x, sub(a0, b0)) +
+                  !same_float(d.y, sub(a1, b1)) + !same_float(m.x, mul(a0, b0)) + !same_float(m.y, mul(a1, b1)) +
+                  !same_float(ms.x, mul(a0, b0)) + !same_float(ms.y, mul(a1, b0)) +
+                  !same_float(ma.x, add(mul(a0, b0), a0)) + !same_float(ma.y, add(mul(a1, b1), a1));
+  }
+  if (bad_rcp) atomicAdd(counts + 0, (unsigned long long)bad_rcp);
+  if (bad_sqrt) atomicAdd(counts + 1, (unsigned long long)bad_sqrt);
+  if (bad_packed) atomicAdd(counts + 2, (unsigned long long)bad_packed);
+}
+
 // uniform initial state, every padded row (d2q9-bgk.c:880-902)
 __global__ void fill_planes(float* buf, size_t plane, float w0, float w1, float w2)
 {

@@ -68,6 +68,13 @@ def free_cells_inv(obstacles: np.ndarray) -> np.float32:
     return np.float32(library().lbm_b200_free_cells_inv(_ip(ob), ob.size))
 
 
+def selftest(device: int = 0):
+    """(rcp mismatches, sqrt mismatches, packed-arithmetic mismatches) of lbm_b200_selftest; all must be 0."""
+    counts = (ctypes.c_ulonglong * 3)()
+    _check(library().lbm_b200_selftest(device, counts))
+    return tuple(int(c) for c in counts)
+
+
 def device_count() -> int:
     return int(library().lbm_b200_device_count())
 

@@ -33,7 +33,7 @@ def test_no_torch_or_cxx_types_in_the_header():
 
 
 def test_abi_version(pkg):
-    assert pkg.library().lbm_b200_abi_version() == 1
+    assert pkg.library().lbm_b200_abi_version() == 2          # r02: _ex constructors, selftest
 
 
 def test_oracle_is_not_linked_into_the_product(pkg):
@@ -111,3 +111,49 @@ def test_band_plan_of_the_fused_kernel(pkg):
     assert plan(2048, 2048, 0)[1] == 16 and plan(4096, 4096, 0)[1] == 64
     assert plan(16384, 16384, 0)[1] in (64, 96)
     assert lib.lbm_b200_plan_bands(1, 1024, 0, 148, None, None) != 0
+
+
+def test_packed_multiplies_cannot_be_contracted(pkg):
+    """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, which would break bit-identity
+    with the reference.  The library issues every packed multiply as fma(a, b, -0.0f) with an addend the compiler
+    cannot see through (csrc/lbm_cell.cuh): in the SASS every FFMA2 must carry one broadcast scalar register as its
+    addend, and no FMUL2 may exist."""
+    import shutil
+    import sass_hist
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    seen = 0
+    for name, instrs in sass_hist.functions(pkg.LIB_PATH).items():
+        assert sass_hist.unsafe_packed(instrs) == [], name
+        seen += sum(1 for i in instrs if sass_hist.opcode(i) in ("FFMA2", "FADD2"))
+    assert seen > 1000                                        # the packed path is really in the library
+
+
+def test_bench_parity_fixture_matches_the_oracle(pkg, oracle):
+    """tests/golden/ring_parity.npz is what tests/golden/make_ring_parity.py would write today (oracle unchanged,
+    obstacle generator unchanged) -- bench.py trusts it without a CPU solver on the product path."""
+    par = pkg.parity
+    for n in par.RANK_COUNTS:
+        ny = par.ROWS_PER_RANK * n
+        ob = par.obstacles(par.PERIOD, ny, n)
+        cells = oracle.init_cells(par.PERIOD, ny, par.DENSITY)
+        inv = pkg.decks.free_cells_inv(par.PERIOD * ny - int(ob.sum()))
+        av = oracle.run(cells, ob, par.STEPS, par.DENSITY, par.ACCEL, par.OMEGA, inv)
+        want_cells, want_av = par.expected(n)
+        assert np.array_equal(cells.view(np.uint32), want_cells.view(np.uint32))
+        assert np.array_equal(av.view(np.uint32), want_av.view(np.uint32))
+        # a wider grid holds the same solution tiled: compare_slab accepts it, and notices a single flipped bit
+        wide = np.tile(want_cells, (1, 4, 1))
+        assert par.compare_slab(wide[par.ROWS_PER_RANK * (n - 1):], par.ROWS_PER_RANK * (n - 1), n) == 0
+        wide.view(np.uint32)[3, 100, 4] ^= 1
+        assert par.compare_slab(wide, 0, n) == 1
+
+
+def test_obstacle_bit_packing_layout(pkg):
+    ob = np.zeros((3, 70), np.int32)
+    ob[1, 33] = 1
+    ob[2, 69] = 5
+    ob[0, 0] = 1
+    bits_ = pkg.pack_obstacle_bits(ob)
+    assert bits_.shape == (3, 3) and bits_.dtype == np.uint32
+    assert bits_[0, 0] == 1 and bits_[1, 1] == 2 and bits_[2, 2] == 1 << 5 and int(bits_.sum()) == 1 + 2 + 32

@@ -104,3 +104,41 @@ def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
     ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     assert np.array_equal(bits(cells), bits(ref))
     assert np.max(np.abs(data["av"] - ref_av) / ref_av) < 1e-4
+
+
+@pytest.mark.parametrize("deck", ["128x256", "1024x1024"])
+def test_c_launcher_one_process_per_gpu(pkg, tmp_path, deck):
+    """bin/d2q9-bgk-mp -np N: the C program that forks one rank per GPU and wires the ring with lbm_b200_create_slab_ex /
+    ipc_export / ipc_connect -- no Python anywhere.  Its final_state.dat must be byte-identical to the strict build of
+    the reference (sha256 fixture), whatever the number of ranks."""
+    import hashlib
+    import json
+    from conftest import GOLDEN, deck_paths
+    n = min(pkg.device_count(), 4)
+    need_gpus(pkg, 2)
+    pfile, ofile = deck_paths(deck)
+    want = json.load(open(os.path.join(GOLDEN, "ref_strict.json")))["decks"][deck]
+    res = subprocess.run([pkg.EXE_PATH + "-mp", "-np", str(n), pfile, ofile], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = res.stdout.splitlines()
+    assert lines[0] == "==done==" and lines[1].startswith("Reynolds number:\t\t")
+    assert hashlib.sha256((tmp_path / "final_state.dat").read_bytes()).hexdigest() == want["final_state_sha256"]
+    assert lines[1].split()[-1] == want["reynolds"]
+
+
+def test_one_rank_alone_times_out(pkg):
+    """Two ranks on two GPUs, only rank 0 runs: its kernels give up waiting for rank 1's halo rows after
+    spin_timeout_ms and lbm_b200_sync reports LBM_B200_ERR_STATE instead of hanging the GPU."""
+    need_gpus(pkg, 2)
+    nx, ny = 256, 32
+    obstacles = np.zeros((ny, nx), np.int32)
+    obstacles[0] = obstacles[-1] = 1
+    sim = pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=2, devices=[0, 1])
+    try:
+        sim.set_option("spin_timeout_ms", 100)
+        sim.set_option("debug_skip_slab", 1)
+        with pytest.raises(pkg.LBMError) as err:
+            sim.run(6)
+        assert "waiting for halo" in str(err.value)
+    finally:
+        sim.close()

@@ -1,0 +1,127 @@
+"""Round-2 additions on one B200: the arithmetic self-test, obstacle map formats, CUDA-graph replay across runs of
+growing length (the graphs captured a freed av_vels pointer), the bounded halo wait with its error
+report, back-to-back runs on a fused ring, and bench.py's parity case against the committed expectation."""
+import numpy as np
+import pytest
+
+from conftest import bits, random_cells, random_obstacles
+
+pytestmark = pytest.mark.gpu
+
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
+
+
+def test_arithmetic_selftest(pkg):
+    """rcp_fast / sqrt_fast against __frcp_rn / __fsqrt_rn over every float of the fast range, packed fp32x2
+    add / sub / mul against the scalar IEEE operations over 2^28 operand pairs of arbitrary bit patterns."""
+    assert pkg.selftest(0) == (0, 0, 0)
+
+
+@pytest.mark.parametrize("fmt", ["uint8", "bits"])
+@pytest.mark.parametrize("n_slabs", [1, 3])
+def test_obstacle_formats_give_the_same_run(pkg, fmt, n_slabs):
+    """lbm_b200_create_ex: one byte per cell and one bit per cell (nx not a multiple of 32: padding bits set on
+    purpose) against the reference's int per cell -- same mask, same free-cell count, same bits after 30 steps."""
+    rng = np.random.default_rng(7)
+    nx, ny, iters = 300, 41, 30
+    obstacles = random_obstacles(rng, ny, nx, 0.08)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, device=0) as sim:
+        want_av = sim.run(iters)
+        want = sim.get_cells()
+    if fmt == "uint8":
+        ob = (obstacles * 7).astype(np.uint8)                 # any non-zero value blocks
+    else:
+        ob = pkg.pack_obstacle_bits(obstacles)
+        ob[:, -1] |= np.uint32(0xFFFFFFFF) << np.uint32(nx % 32)   # garbage in the padding bits past nx
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, ob, n_slabs=n_slabs, device=0, obstacles_format=fmt) as sim:
+        av = sim.run(iters)
+        assert np.array_equal(bits(sim.get_cells()), bits(want))
+        assert np.array_equal(bits(av), bits(want_av))        # same free-cell count => same scaling, bit for bit
+
+
+@pytest.mark.parametrize("n_slabs", [1, 2])
+def test_graph_replay_survives_a_longer_second_run(pkg, oracle, n_slabs):
+    """graph_steps=16, run(40) then run(400): the second run reallocates the device av_vels array; the graphs that
+    captured the old pointer must be rebuilt (r1: they wrote the averages into freed memory)."""
+    rng = np.random.default_rng(11)
+    nx, ny = 128, 48
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    ref = oracle.init_cells(nx, ny, DENSITY)
+    inv = pkg.free_cells_inv(obstacles)
+    ref_av = oracle.run(ref, obstacles, 440, DENSITY, ACCEL, OMEGA, inv)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, device=0) as sim:
+        sim.set_option("graph_steps", 16)
+        av = np.concatenate([sim.run(40), sim.run(400)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
+@pytest.mark.parametrize("fused2", [0, 1])
+def test_a_missing_neighbour_times_out_instead_of_hanging(pkg, fused2):
+    """One slab of a two-slab ring is never launched (test hook debug_skip_slab): its neighbour's second pass waits
+    for halo rows that never come.  The wait gives up after spin_timeout_ms, the run drains, and sync reports
+    LBM_B200_ERR_STATE naming the exchange -- where the reference would sit in MPI_Waitall (d2q9-bgk.c:364)."""
+    nx, ny = 256, 32
+    obstacles = np.zeros((ny, nx), np.int32)
+    obstacles[0] = obstacles[-1] = 1
+    sim = pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=2, device=0)
+    try:
+        sim.set_option("fused2", fused2)
+        sim.set_option("spin_timeout_ms", 50)
+        sim.set_option("debug_skip_slab", 1)
+        with pytest.raises(pkg.LBMError) as err:
+            sim.run(8)
+        text = str(err.value)
+        assert text.startswith("[4]") and "waiting for halo" in text and "neighbour" in text
+        with pytest.raises(pkg.LBMError):                       # the handle stays failed
+            sim.run(2)
+    finally:
+        sim.close()
+
+
+def test_back_to_back_runs_on_a_fused_ring(pkg, oracle):
+    """enqueue, enqueue, enqueue without a sync in between: the body-force pre-pass of every run (also the one on the
+    halo copy of the driven row, ordered by the strip flags) must see the previous run's last pushes."""
+    rng = np.random.default_rng(5)
+    nx, ny = 480, 37
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    ref = oracle.init_cells(nx, ny, DENSITY)
+    oracle.run(ref, obstacles, 7 + 6 + 5 + 2, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=4, device=0) as sim:
+        sim.set_option("band_rows", 4)
+        sim.set_option("fused2", 1)
+        for it in (7, 6, 5, 2):
+            sim.enqueue(it)
+        sim.sync()
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_bench_parity_case_on_one_device(pkg, n):
+    """What bench.py checks before its timed region, here with the N slabs of a whole-domain handle on one device:
+    the committed expectation (tests/golden/ring_parity.npz) is met bit for bit by the two-steps-per-pass kernel."""
+    par = pkg.parity
+    nx, ny = 256, par.ROWS_PER_RANK * n
+    ob = par.obstacles(nx, ny, n)
+    with pkg.Simulation(nx, ny, par.DENSITY, par.ACCEL, par.OMEGA, ob, n_slabs=n, device=0) as sim:
+        sim.set_option("fused2", 1)
+        assert sim.get_option("kernel") == 5
+        for it in par.RUNS:
+            sim.enqueue(it)
+        sim.sync()
+        assert par.compare_slab(sim.get_cells(), 0, n) == 0
+
+
+def test_final_state_chunks_match_the_oracle(pkg, oracle):
+    """get_final_state in overlapped row chunks (>= 64 rows): the same four fields as write_values computes."""
+    rng = np.random.default_rng(3)
+    nx, ny, iters = 128, 203, 25
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    ref = oracle.init_cells(nx, ny, DENSITY)
+    oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    want = oracle.final_state(ref, obstacles, DENSITY)
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+        sim.run(iters)
+        got = sim.final_state()
+    for g, w in zip(got, want):
+        assert np.array_equal(bits(g), bits(w))

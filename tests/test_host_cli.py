@@ -63,3 +63,19 @@ def test_no_gpu_is_a_loud_failure_not_a_fallback(pkg, tmp_path):
     assert res.returncode == 1
     assert "no CUDA device available" in res.stderr
     assert not os.path.exists(tmp_path / "av_vels.dat")
+
+
+def test_mp_launcher_usage_and_no_device_failure(pkg, tmp_path):
+    """d2q9-bgk-mp (one process per GPU, the reference's mpirun -np N): usage text, and -- on a box without a GPU --
+    every rank dies with the library's message, the launcher reports failure and nobody is left in a barrier."""
+    exe = pkg.EXE_PATH + "-mp"
+    assert os.path.exists(exe)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 1 and res.stderr == f"Usage: {exe} [-np N] <paramfile> <obstaclefile>\n"
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is visible: the launcher's run is covered by tests/test_gpu_multi.py")
+    pfile, ofile = deck_paths("128x128")
+    res = subprocess.run([exe, "-np", "2", pfile, ofile], capture_output=True, text=True, cwd=tmp_path, timeout=60)
+    assert res.returncode == 1
+    assert "no CUDA device available (there is no CPU fallback)" in res.stderr
+    assert not (tmp_path / "av_vels.dat").exists()
