@@ -325,8 +325,8 @@ def bench_ours(args, pkg):
 
     nx, n = args.nx, world
     ips, K, W = args.timesteps, args.steps, args.warmup
-    tuning_keys = ("kernel", "graph_steps", "ctas_per_sm", "min_ctas", "fused2", "band_rows", "prefetch_rows", "cache_hint")
-    pingpong_only = ("kernel", "min_ctas", "fused2", "band_rows", "prefetch_rows")
+    tuning_keys = ("kernel", "graph_steps", "ctas_per_sm", "min_ctas", "fused2", "band_rows", "prefetch_rows", "cache_hint", "fused_deep")
+    pingpong_only = ("kernel", "min_ctas", "fused2", "band_rows", "prefetch_rows", "fused_deep")
 
     def make_sim(obstacles, fmt, rows, first, ny_global, ranks=n, inv=None):
         """One slab per rank on the CUDA IPC ring (ranks > 1) or the whole grid on this GPU, tuned as asked."""
@@ -594,6 +594,7 @@ def main():
     ap.add_argument("--band-rows", dest="band_rows", type=int, default=None)
     ap.add_argument("--prefetch-rows", dest="prefetch_rows", type=int, default=None, help="kernel 5: L2 prefetch distance in rows")
     ap.add_argument("--cache-hint", dest="cache_hint", type=int, default=None)
+    ap.add_argument("--fused-deep", dest="fused_deep", type=int, default=None, help="kernel 5 on one GPU: two staging rows, 12 warps per SM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the bit-exact parity case before the timed region")
     ap.add_argument("--no-e2e", action="store_true", help="skip the whole-job (host buffers in, host buffers out) measurement")

@@ -123,6 +123,7 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
+  long opt_fused_deep = 1;              // kernel 5: two staging rows, 3 CTAs x 4 warps per SM (+3 %, profiles/r02_fused2.md)
   long opt_prefetch_rows = 0;           // kernel 5: L2 prefetch distance in rows (0 = off: measured slower, profiles/r02_fused2.md)
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
   long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
@@ -221,8 +222,10 @@ bool want_fused2(const lbm_b200* h)
   return h->opt_fused2 == 1 || (long)h->nx * h->ny / h->n_ranks >= kFusedAutoMinCells;
 }
 
-constexpr int kFusedWarps = 8;
-constexpr size_t kFusedSmem = (size_t)kFusedWarps * lbm::kFusedWarpFloat4 * sizeof(float4);
+// kernel 5 launch shapes: 8 warps per CTA, 2 CTAs per SM, one staging row -- or ("deep", single-GPU handles) 4 warps
+// per CTA, 3 CTAs per SM, two staging rows
+constexpr int fused_warps(bool deep) { return deep ? 4 : 8; }
+constexpr size_t fused_smem(bool deep) { return (size_t)fused_warps(deep) * lbm::fused_warp_float4(deep) * sizeof(float4); }
 
 void plan(lbm_b200* h)
 {
@@ -239,7 +242,8 @@ void plan(lbm_b200* h)
       s.fused_bands = bands;
       s.fused_band_rows = per;
       const long items = (long)h->fused_strips * bands;
-      s.fused_grid = (int)std::min<long>((items + kFusedWarps - 1) / kFusedWarps, 1L << 30);
+      const int wpc = fused_warps(h->opt_fused_deep != 0);
+      s.fused_grid = (int)std::min<long>((items + wpc - 1) / wpc, 1L << 30);
       if (h->opt_ctas_per_sm > 0) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
@@ -630,7 +634,10 @@ int allow_fused_smem(Slab& s)
 {
   if (s.fused_attr) return LBM_B200_OK;
   CUDA_TRY(cudaSetDevice(s.device));
-  const int bytes = (int)kFusedSmem;
+  const int bytes = (int)fused_smem(false);
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
+  CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<3, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
   CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(lbm::steps2_strip<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -658,9 +665,12 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
     g.fold_last = fold_last ? 1 : 0;
     g.partial_stride = s.per_step;
     g.prefetch_rows = (int)h->opt_prefetch_rows;
-    const dim3 grid(s.fused_grid), block(kFusedWarps * 32);
+    const bool deep = h->opt_fused_deep != 0;
+    const size_t kFusedSmem = fused_smem(deep);
+    const dim3 grid(s.fused_grid), block(fused_warps(deep) * 32);
     if (h->n_ranks == 1) {
-      if (h->opt_cache_hint == 1) lbm::steps2_strip<1, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      if (deep) lbm::steps2_strip<0, false, false, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      else if (h->opt_cache_hint == 1) lbm::steps2_strip<1, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
       else if (h->opt_cache_hint == 2) lbm::steps2_strip<2, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
       else lbm::steps2_strip<0, false, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
     } else {
@@ -673,8 +683,13 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
       g.south_rows = s.south.rows;
       g.north_rows = s.north.rows;
       // (halo rows are written by the neighbours: L2-coherent loads, HINT 3 -- irrelevant for cp.async.cg)
-      if (single) lbm::steps2_strip<3, true, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
-      else lbm::steps2_strip<3, true, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      if (deep) {
+        if (single) lbm::steps2_strip<3, true, true, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+        else lbm::steps2_strip<3, true, false, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      } else {
+        if (single) lbm::steps2_strip<3, true, true><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+        else lbm::steps2_strip<3, true, false><<<grid, block, kFusedSmem, s.stream>>>(a, g);
+      }
     }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -827,6 +842,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
   if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
+  if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = atol(e) != 0;
   if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
 }
 
@@ -1576,6 +1592,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "staging_bytes")) {
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
     h->opt_staging_bytes = value;
+  } else if (!strcmp(key, "fused_deep")) {
+    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "fused_deep must be 0 or 1");
+    h->opt_fused_deep = value;
   } else if (!strcmp(key, "prefetch_rows")) {
     if (value < 0 || value > 16) return fail(LBM_B200_ERR_ARG, "prefetch_rows must be 0 .. 16");
     h->opt_prefetch_rows = value;
@@ -1616,6 +1635,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
   else if (!strcmp(key, "prefetch_rows")) *value = h->opt_prefetch_rows;
+  else if (!strcmp(key, "fused_deep")) *value = h->opt_fused_deep;
   else if (!strcmp(key, "spin_timeout_ms")) *value = h->opt_spin_timeout_ms;
   else if (!strcmp(key, "debug_skip_slab")) *value = h->opt_debug_skip_slab;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;

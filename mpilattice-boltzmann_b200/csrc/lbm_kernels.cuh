@@ -689,6 +689,7 @@ __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Ring slabs: one flag word per 120-column strip and direction, same protocol as warp_peer_wait/warp_peer_signal.
 __device__ __forceinline__ void strip_wait(const StepArgs& a, const unsigned* flags, unsigned dir, int strip, int strips, int lane)
@@ -714,7 +715,10 @@ __device__ __forceinline__ void strip_signal(const StepArgs& a, unsigned* flags,
 // through warp shuffles -- so neither a warp barrier nor an mbarrier sits between the producers and consumers.
 constexpr int kRingPlanes = 6;                                   // ring order: planes 0, 1, 3, 2, 5, 6
 constexpr int kRingSlot = kRingPlanes * 32;                      // float4 per ring row
-constexpr int kFusedWarpFloat4 = 3 * kRingSlot + 9 * 32;
+constexpr int kStageSlot = 9 * 32;                               // float4 per staging row
+// DEEP: two staging rows (the copy runs two rows ahead of the arithmetic) at 3 CTAs x 4 warps per SM and up to 168
+// registers, instead of one staging row at 2 CTAs x 8 warps and 128 registers.
+__host__ __device__ constexpr int fused_warp_float4(bool deep) { return 3 * kRingSlot + (deep ? 2 : 1) * kStageSlot; }
 
 // 128-bit accesses that deliver / take two packed pairs in 64-bit registers (no re-packing around the access)
 __device__ __forceinline__ void lds2(const float4* p, f2& a, f2& b)
@@ -791,14 +795,14 @@ __device__ __forceinline__ float collide_quad_generic(f2 (&p)[9], f2 (&q)[9], un
 // column and are simply wrong -- nobody reads them: the second step of the own columns needs first-step columns
 // -1 .. 120 of the strip only.  (A shuffle without a source lane returns the lane's own value, so the unused cells
 // stay finite.)
-template <int HINT, bool PEER, bool SINGLE>
-__global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const FusedArgs g)
+template <int HINT, bool PEER, bool SINGLE, bool DEEP = false>
+__global__ void __launch_bounds__(DEEP ? 128 : 256, DEEP ? 3 : 2) steps2_strip(const StepArgs a, const FusedArgs g)
 {
   extern __shared__ float4 fused_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  float4* const ring = fused_smem + (size_t)warp * kFusedWarpFloat4 + lane;   // this lane's cells of [3][6][32]
-  const float4* const stage = ring + 3 * kRingSlot;                           // this lane's cells of [9][32]
-  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+  float4* const ring = fused_smem + (size_t)warp * fused_warp_float4(DEEP) + lane;   // this lane's cells of [3][6][32]
+  const float4* const stage0 = ring + 3 * kRingSlot;                          // this lane's cells of [1 or 2][9][32]
+  const unsigned stage0_s = (unsigned)__cvta_generic_to_shared(stage0);
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
@@ -863,6 +867,8 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         }
       };
       for (int d = 1; d < g.prefetch_rows; d++) prefetch_row(q_y + d);
+      unsigned stage_s = stage0_s;                            // where the next copy goes / the next first step reads
+      const float4* stage = stage0;
       auto issue = [&]() -> unsigned {
         if (g.prefetch_rows > 0) prefetch_row(q_y + g.prefetch_rows);
         const float* pc = src + ((unsigned)q_c * (unsigned)nx + (unsigned)gx);
@@ -878,6 +884,7 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
         cp_async16(stage_s + 7 * 512, pn + 7 * P);
         cp_async16(stage_s + 8 * 512, pn + 8 * P);
         cp_async_commit();
+        if (DEEP) stage_s ^= (stage0_s ^ (stage0_s + kStageSlot * 16));      // the other staging row next time
         // obstacle words: the slab's own rows, then (ring) the southern and the northern neighbour's adjacent row
         const int mrow = EDGE ? ((q_y < 0) ? rows : (q_y >= rows ? rows + 1 : q_y)) : q_c - 1;
         const unsigned word = __ldg(mask_x + (unsigned)mrow * (unsigned)a.mask_row_words);   // used a whole row later: no stall here
@@ -929,13 +936,16 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       //      and cell 3 + the value shuffled in for cell 0 fill the second half (mirrored for east-moving ones), so
       //      only the three unshifted planes need register moves.  Results keep that rotated order (columns 1,2,3,0
       //      of the group): six planes go into ring row `slot`, planes 4,7,8 come back in registers.  With `ahead`
-      //      the copy for row y+1 is issued as soon as the staging row has been read; its obstacle word is returned.
-      auto step1 = [&](const int y, const unsigned mword, float4* const slot, const bool ahead, const bool count,
-                       f2 (&kp)[3], f2 (&kq)[3]) -> unsigned {
-        cp_async_wait_all();
+      //      the next copy (one row ahead; DEEP: two) is issued as soon as the staging row has been read; its obstacle
+      //      word is returned.
+      auto step1 = [&](const int y, const unsigned mword, float4* const slot, const bool ahead, const bool more_copies_pending,
+                       const bool count, f2 (&kp)[3], f2 (&kq)[3]) -> unsigned {
+        // (DEEP: the copy for the row after this one is in flight as well and may stay so)
+        if (DEEP && more_copies_pending) cp_async_wait_but_one(); else cp_async_wait_all();
         f2 lo[9], hi[9];                                         // lo = columns 0,1 of the lane's group, hi = columns 2,3
 #pragma unroll
         for (int k = 0; k < 9; k++) lds2(stage + k * 32, lo[k], hi[k]);
+        if (DEEP) stage = (stage == stage0) ? stage0 + kStageSlot : stage0;
         const float up1 = __shfl_up_sync(0xffffffffu, hi2(hi[1]), 1);
         const float up5 = __shfl_up_sync(0xffffffffu, hi2(hi[5]), 1);
         const float up8 = __shfl_up_sync(0xffffffffu, hi2(hi[8]), 1);
@@ -1026,25 +1036,27 @@ __global__ void __launch_bounds__(256, 2) steps2_strip(const StepArgs a, const F
       };
 
       f2 kp[3], kq[3];
-      if (SINGLE) {
-        unsigned word = issue();
+      // Rows r0 .. r_last get their first step (yb-1 .. ye; SINGLE: yb .. ye-1); the copies run D rows ahead.
+      // (w_c, w_n, w_nn = obstacle words of the rows of the next second step, the next first step and -- DEEP -- the
+      // first step after that.)
+      constexpr int D = DEEP ? 2 : 1;
+      const int r0 = SINGLE ? yb : yb - 1, r_last = SINGLE ? ye - 1 : ye;
+      unsigned w_c = 0u, w_n = issue(), w_nn = 0u;
+      if (DEEP && r0 + 1 <= r_last) w_nn = issue();
+      float4 *s_s = ring, *s_c = ring + kRingSlot, *s_n = ring + 2 * kRingSlot;
 #pragma unroll 1
-        for (int y = yb; y < ye; y++) word = step1(y, word, ring, y + 1 < ye, owned, kp, kq);
-      } else {
-        // rows yb-1 .. ye get their first step; every owned row gets its second step as soon as the first step of
-        // the row above it has run.  (w_c, w_n = obstacle words of the rows the next second / first step is for.)
-        unsigned w_c = 0u, w_n = issue();
-        float4 *s_s = ring, *s_c = ring + kRingSlot, *s_n = ring + 2 * kRingSlot;
-#pragma unroll 1
-        for (int r = yb - 1; r <= ye; r++) {
-          const unsigned w_nn = step1(r, w_n, s_n, r < ye, owned && r >= yb && r < ye, kp, kq);
+      for (int r = r0; r <= r_last; r++) {
+        const unsigned w_new = step1(r, w_n, s_n, r + D <= r_last, DEEP && r + 1 <= r_last, owned && r >= yb && r < ye, kp, kq);
+        if (!SINGLE) {
+          // every owned row gets its second step as soon as the first step of the row above it has run
           if (r > yb) {
             step2(r - 1, w_c, s_s, s_c, kp, kq);
             publish(r - 1);
           }
-          w_c = w_n; w_n = w_nn;
           float4* const t = s_s; s_s = s_c; s_c = s_n; s_n = t;
         }
+        w_c = w_n;
+        if (DEEP) { w_n = w_nn; w_nn = w_new; } else w_n = w_new;
       }
     };
     if (PEER && (band == 0 || band == g.bands - 1)) run_item(std::true_type{});

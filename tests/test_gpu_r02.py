@@ -125,3 +125,24 @@ def test_final_state_chunks_match_the_oracle(pkg, oracle):
         got = sim.final_state()
     for g, w in zip(got, want):
         assert np.array_equal(bits(g), bits(w))
+
+
+@pytest.mark.parametrize("iters", [20, 21])
+def test_fused_deep_variant_is_bit_identical(pkg, oracle, iters):
+    """Kernel 5 with two staging rows (copies two rows ahead, 3 CTAs x 4 warps per SM): same bits, ragged bands,
+    obstacles, an odd tail."""
+    rng = np.random.default_rng(17)
+    nx, ny = 500, 77
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    for band in (0, 5):
+        with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+            sim.set_option("fused2", 1)
+            sim.set_option("fused_deep", 1)
+            sim.set_option("band_rows", band)
+            sim.set_cells(cells0)
+            av = sim.run(iters)
+            assert np.array_equal(bits(sim.get_cells()), bits(ref))
+            assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
