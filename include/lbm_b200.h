@@ -181,14 +181,26 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
 
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
  *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit); reads back 3
- *                   when the resident variant of kernel 2 is in use, 4 on an in-place handle and 5 when two
- *                   timesteps are fused per pass ("fused2")
+ *                   when the resident variant of kernel 2 is in use, 4 on an in-place handle, 5 when two
+ *                   timesteps are fused per pass ("fused2") and 6 when the grid lives in a cluster's shared memory
  *   "fused2"        two timesteps per pass over HBM (kernel 5: the first step of a 120-column strip goes into a
  *                   shared-memory ring, the second comes out of it; half the DRAM traffic per step, bit-identical
  *                   results; ring slabs keep two halo rows per side and exchange once per pass).  1 = on where it
  *                   applies (ping-pong handle, nx % 4 == 0, nx >= 240, >= 4 rows per slab), 0 = off, -1 = automatic
  *                   (on from 2^22 cells per GPU).  Reads back whether it is in use; "kernel" then reads 5.
  *                   On a multi-process ring set it on every rank while the ring is idle.
+ *   "cluster"       kernel 6: the whole grid resident in the shared memory of ONE 16-CTA thread-block cluster for up
+ *                   to 256 timesteps per launch, halo rows read from the neighbour CTA over distributed shared
+ *                   memory, one hardware cluster barrier per step (for launch-latency-bound decks: 128 x 128 and
+ *                   128 x 256 fit; single-GPU ping-pong handles with ny % 16 == 0).  1 = wherever it fits, 0 = never,
+ *                   -1 = automatic (where it fits and no other kernel / launch mode was asked for).  Reads back
+ *                   whether it is in use; "kernel" then reads 6.
+ *   "fused_deep"    kernel 5: 1 (default) = two staging rows, the copy runs two rows ahead of the arithmetic, 3 CTAs
+ *                   x 4 warps per SM; 0 = one staging row, 2 CTAs x 8 warps per SM
+ *   "prefetch_rows" kernel 5: bulk L2 prefetch this many rows ahead of the copy (default 0 = off: measured slower)
+ *   "spin_timeout_ms"  how long a kernel of a ring slab waits for a neighbour's halo flag before it gives up and
+ *                   lbm_b200_sync reports LBM_B200_ERR_STATE (default 30000)
+ *   "debug_skip_slab"  test hook: the step kernels of this slab of a whole-domain handle are not launched
  *   "band_rows"     rows per work item of kernel 5 (0 = automatic)
  *   "inplace"       read-only: 1 on a handle made by lbm_b200_create_inplace
  *   "staging_bytes" in-place handles: size of the device staging buffer that get_cells / set_cells /

@@ -123,6 +123,7 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
+  long opt_cluster = -1;                // kernel 6: -1 automatic, 0 never, 1 wherever it fits
   long opt_fused_deep = 1;              // kernel 5: two staging rows, 3 CTAs x 4 warps per SM (+3 %, profiles/r02_fused2.md)
   long opt_prefetch_rows = 0;           // kernel 5: L2 prefetch distance in rows (0 = off: measured slower, profiles/r02_fused2.md)
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
@@ -131,6 +132,8 @@ struct lbm_b200 {
   bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
   int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
+  bool cluster = false;                 // the grid lives in the shared memory of one 16-CTA cluster (kernel 6)
+  int cluster_threads = 0;
   int last_iters = 0;
   int graph_len = 0;
   long launches = 0;                    // kernels launched by the last enqueue (all slabs)
@@ -207,6 +210,44 @@ bool want_resident(const lbm_b200* h)
   return h->opt_resident == 1 || (cells >= kResidentAutoMinCells && cells <= kGraphAutoCells);
 }
 
+// Kernel 6: single-GPU ping-pong handles whose grid fits twice into the shared memory of one 16-CTA cluster.
+size_t cluster_smem_bytes(const lbm_b200* h) { return 2 * 9 * sizeof(float) * (size_t)(h->ny / lbm::kClusterCtas) * h->nx; }
+
+bool want_cluster(lbm_b200* h)
+{
+  if (h->opt_cluster == 0 || h->n_ranks != 1 || h->slabs.size() != 1 || h->inplace) return false;
+  // automatic: only where the caller has not asked for a particular kernel / launch mode
+  if (h->opt_cluster < 0 && (h->opt_kernel != 0 || h->opt_resident == 1 || h->opt_graph_steps >= 0 || h->opt_fused2 == 1)) return false;
+  if (h->ny % lbm::kClusterCtas != 0 || h->ny / lbm::kClusterCtas < 1) return false;
+  const size_t bytes = cluster_smem_bytes(h);
+  int max_smem = 0, cluster_ok = 0;
+  const int dev = h->slabs[0].device;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&cluster_ok, cudaDevAttrClusterLaunch, dev);
+  if (!cluster_ok || bytes > (size_t)max_smem) return false;
+  const int ncell = (h->ny / lbm::kClusterCtas) * h->nx;
+  h->cluster_threads = std::min(1024, (ncell + 31) / 32 * 32);
+  // can one cluster of 16 such CTAs be resident?  (non-portable cluster size: opt in first)
+  cudaSetDevice(dev);
+  if (cudaFuncSetAttribute(lbm::steps_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(lbm::steps_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(lbm::kClusterCtas); cfg.blockDim = dim3(h->cluster_threads); cfg.dynamicSmemBytes = bytes;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = lbm::kClusterCtas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, lbm::steps_cluster, &cfg) != cudaSuccess || clusters < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
 // Two timesteps per pass (kernel 5): ping-pong handles whose rows are at least two strips wide; on a ring every
 // slab needs four rows (the driven row ny-2 must not be a row a neighbour recomputes).
 bool want_fused2(const lbm_b200* h)
@@ -231,6 +272,8 @@ void plan(lbm_b200* h)
 {
   h->resident = want_resident(h);
   h->fused2 = want_fused2(h);
+  h->cluster = !(h->fused2 && h->opt_fused2 == 1) && want_cluster(h);
+  if (h->cluster) h->resident = h->fused2 = false;
   if (h->fused2) {
     h->resident = false;
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
@@ -256,6 +299,7 @@ void plan(lbm_b200* h)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
       s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_grid : 0);
+      if (h->cluster) s.per_step = std::max(s.per_step, lbm::kClusterCtas * (h->cluster_threads / 32));
     } else if (use_vec4(h)) {
       // one launch per step and slab: edge rows first, then the interior (csrc/lbm_kernels.cuh)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
@@ -842,6 +886,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_RESIDENT")) h->opt_resident = atol(e);
   if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
+  if (const char* e = getenv("LBM_B200_CLUSTER")) h->opt_cluster = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = atol(e) != 0;
   if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
 }
@@ -1239,7 +1284,7 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
   }
   if (av_moved) destroy_graphs(h);                   // they captured the old av_vels pointer
   int glen = (int)h->opt_graph_steps;
-  if (h->resident || h->fused2) glen = 0;
+  if (h->resident || h->fused2 || h->cluster) glen = 0;
   if (glen < 0) {
     // auto: grids whose step kernel is launch-latency bound (a few microseconds) are replayed
     // from CUDA graphs -- measured 4.1 -> 2.7 us per step on the 128..256-wide decks
@@ -1293,6 +1338,37 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       }
     }
     int t = 0;
+    if (h->cluster) {
+      // the grid lives in one cluster's shared memory for up to kChunkSteps steps per launch (kernel 6)
+      Slab& s = h->slabs[0];
+      CUDA_TRY(cudaSetDevice(s.device));
+      const size_t bytes = cluster_smem_bytes(h);
+      while (t < iters) {
+        const int n = std::min(kChunkSteps, iters - t);
+        lbm::ClusterArgs ca{};
+        ca.in = s.buf[h->cur]; ca.out = s.buf[h->cur ^ 1]; ca.plane = s.plane;
+        ca.mask = s.mask; ca.mask_row_words = h->mask_row_words;
+        ca.nx = h->nx; ca.rows_per_cta = h->ny / lbm::kClusterCtas;
+        ca.steps = n; ca.fold_last = (t + n != iters) ? 1 : 0;
+        ca.accel_row = h->ny - 2;
+        ca.c = h->sc;
+        ca.partials = s.partials; ca.partial_stride = s.per_step;
+        CUDA_TRY(cudaMemsetAsync(s.partials, 0, (size_t)n * s.per_step * sizeof(double), s.stream));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(lbm::kClusterCtas); cfg.blockDim = dim3(h->cluster_threads); cfg.dynamicSmemBytes = bytes;
+        cfg.stream = s.stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = lbm::kClusterCtas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, lbm::steps_cluster, ca));
+        h->launches += 2;
+        h->cur ^= 1;                                   // the state always lands in the other buffer
+        int rc = enqueue_reduce(h, n);
+        if (rc) return rc;
+        t += n;
+      }
+    }
     if (h->resident) {
       // many steps per cooperative launch; the buffers swap roles inside the kernel
       Slab& s = h->slabs[0];
@@ -1586,6 +1662,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "fused2")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "fused2 must be -1, 0 or 1");
     h->opt_fused2 = value;
+  } else if (!strcmp(key, "cluster")) {
+    if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster must be -1, 0 or 1");
+    h->opt_cluster = value;
   } else if (!strcmp(key, "band_rows")) {
     if (value < 0 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 0 (automatic) .. 2^20");
     h->opt_band_rows = value;
@@ -1629,7 +1708,8 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
 {
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
-  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->fused2 ? 5 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1)));
+  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->cluster ? 6 : (h->fused2 ? 5 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1))));
+  else if (!strcmp(key, "cluster")) *value = h->cluster ? 1 : 0;
   else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;

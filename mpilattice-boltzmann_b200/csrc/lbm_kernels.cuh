@@ -13,6 +13,7 @@
 //   kernel 3  steps_resident  kernel 2 in a cooperative many-steps-per-launch loop (launch-latency-bound grids)
 //   kernel 4  step_inplace    ONE buffer, AA access pattern (two alternating flavours)
 //   kernel 5  steps2_strip    TWO timesteps per pass over HBM through a shared-memory ring (default for big grids)
+//   kernel 6  steps_cluster   the grid resident in the shared memory of one 16-CTA cluster, halo rows over DSMEM
 // Ring slabs (multi-GPU): halo rows are stored straight into the neighbours' buffers over NVLink by the
 // step kernels themselves; flag words (one per 128-cell chunk / 120-column strip) order the exchange.
 #pragma once
@@ -1096,6 +1097,103 @@ __global__ void __launch_bounds__(256, MIN_CTAS) steps_resident(const StepArgs a
     const double acc = vec4_pass<false, 3>(a, src, dst, accel_row);
     block_sum_to(acc, a.partials + (size_t)t * r.partial_stride + blockIdx.x);
     grid.sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 6 ("cluster"): the whole grid RESIDENT IN SHARED MEMORY of one thread-block cluster, many timesteps per
+// launch (first option).  For the shipped 128-wide decks a timestep is ~16 K cell updates: far too
+// little work to hide a kernel launch (2.7 us per step from CUDA graphs) or a grid-wide barrier through L2.  Here
+// kClusterCtas CTAs of one cluster (16: the non-portable maximum) each keep ny/16 rows of all nine planes in
+// their shared memory, twice (ping-pong); a step is one pass of every thread over its cell(s) -- nine loads from
+// shared memory, the three planes of the row above / below an edge row straight out of the NEIGHBOUR CTA's shared
+// memory (distributed shared memory: the halo exchange of d2q9-bgk.c:326-364 becomes a remote load), collide(),
+// nine stores into the other buffer -- and ONE hardware cluster barrier.  Global memory is touched at the start
+// and the end of the launch and for one double per warp and step (the Sigma |m|/rho partials).
+// Per-cell arithmetic: collide()/accelerate() as everywhere, so the populations are bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int kClusterCtas = 16;
+
+struct ClusterArgs {
+  const float* in;       // plane 0 of the buffer that holds the state at launch
+  float* out;            // plane 0 of the buffer that receives the state after `steps` steps
+  size_t plane;          // floats between planes of in / out
+  const uint32_t* mask;
+  int mask_row_words;
+  int nx, rows_per_cta;  // ny = kClusterCtas * rows_per_cta
+  int steps, fold_last;
+  int accel_row;         // 0-based global row ny-2
+  StepConst c;
+  double* partials;      // [steps][partial_stride]: one double per warp of the cluster
+  int partial_stride;
+};
+
+__global__ void __launch_bounds__(1024, 1) steps_cluster(const ClusterArgs a)
+{
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float cluster_smem[];
+  const int rank = (int)cluster.block_rank();
+  const int nx = a.nx, rows = a.rows_per_cta, ncell = rows * nx;   // this CTA's cells
+  float* const buf0 = cluster_smem;                        // [9][ncell]
+  float* const buf1 = cluster_smem + 9 * (size_t)ncell;
+  const int first_row = rank * rows;                       // 0-based global row of local row 0
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+
+  for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+    const size_t g = (size_t)(first_row + 1) * nx + c;     // padded row = global row + 1; rows are contiguous
+#pragma unroll
+    for (int k = 0; k < 9; k++) buf0[k * ncell + c] = __ldg(a.in + k * a.plane + g);
+  }
+  // the rows below local row 0 / above local row rows-1 live in the ring neighbours' shared memory (periodic in y)
+  const int r_s = (rank + kClusterCtas - 1) % kClusterCtas, r_n = (rank + 1) % kClusterCtas;
+  const float* const south0 = cluster.map_shared_rank(buf0, r_s);
+  const float* const south1 = cluster.map_shared_rank(buf1, r_s);
+  const float* const north0 = cluster.map_shared_rank(buf0, r_n);
+  const float* const north1 = cluster.map_shared_rank(buf1, r_n);
+  cluster.sync();
+
+  for (int t = 0; t < a.steps; t++) {
+    const float* const cur = (t & 1) ? buf1 : buf0;
+    float* const nxt = (t & 1) ? buf0 : buf1;
+    const float* const south = (t & 1) ? south1 : south0;
+    const float* const north = (t & 1) ? north1 : north0;
+    const bool fold = (t + 1 < a.steps) || a.fold_last;
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+      const int row = c / nx, x = c - row * nx;
+      const int xw = (x == 0) ? nx - 1 : x - 1, xe = (x + 1 == nx) ? 0 : x + 1;
+      const float* const below = (row > 0) ? cur + (row - 1) * nx : south + (rows - 1) * nx;
+      const float* const above = (row + 1 < rows) ? cur + (row + 1) * nx : north;
+      const float* const here = cur + row * nx;
+      float f[9];
+      f[0] = here[0 * ncell + x];
+      f[1] = here[1 * ncell + xw];
+      f[2] = below[2 * ncell + x];
+      f[3] = here[3 * ncell + xe];
+      f[4] = above[4 * ncell + x];
+      f[5] = below[5 * ncell + xw];
+      f[6] = below[6 * ncell + xe];
+      f[7] = above[7 * ncell + xe];
+      f[8] = above[8 * ncell + xw];
+      const int grow = first_row + row;
+      const bool blocked = (__ldg(a.mask + (size_t)grow * a.mask_row_words + (x >> 5)) >> (x & 31)) & 1u;
+      acc += (double)collide(f, blocked, a.c.omega);
+      if (fold && grow == a.accel_row) accelerate(f, blocked, a.c.aw1, a.c.aw2);
+#pragma unroll
+      for (int k = 0; k < 9; k++) nxt[k * ncell + c] = f[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) a.partials[(size_t)t * a.partial_stride + rank * warps + warp] = acc;
+    cluster.sync();                                        // everybody's new rows are visible cluster-wide
+  }
+
+  const float* const fin = (a.steps & 1) ? buf1 : buf0;
+  for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+    const size_t g = (size_t)(first_row + 1) * nx + c;
+#pragma unroll
+    for (int k = 0; k < 9; k++) a.out[k * a.plane + g] = fin[k * ncell + c];
   }
 }
 

@@ -146,3 +146,40 @@ def test_fused_deep_variant_is_bit_identical(pkg, oracle, iters):
             av = sim.run(iters)
             assert np.array_equal(bits(sim.get_cells()), bits(ref))
             assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (128, 256), (64, 48), (200, 32)])
+def test_cluster_resident_kernel_is_bit_identical(pkg, oracle, shape):
+    """Kernel 6: the grid in the shared memory of one 16-CTA cluster, halo rows over DSMEM.  Random obstacles, an
+    arbitrary initial state, runs that are odd, even, longer than one 256-step launch, and back to back."""
+    nx, ny = shape
+    rng = np.random.default_rng(nx + ny)
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    runs = (7, 300, 1, 256)
+    ref_av = oracle.run(ref, obstacles, sum(runs), DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+        sim.set_option("cluster", 1)
+        assert sim.get_option("kernel") == 6 and sim.get_option("cluster") == 1
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(n) for n in runs])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+        fields = sim.final_state()
+    for g, w in zip(fields, oracle.final_state(ref, obstacles, DENSITY)):
+        assert np.array_equal(bits(g), bits(w))
+
+
+def test_cluster_kernel_is_the_default_for_the_small_decks_only(pkg):
+    ob = np.zeros((128, 128), np.int32)
+    with pkg.Simulation(128, 128, DENSITY, ACCEL, OMEGA, ob, device=0) as sim:
+        assert sim.get_option("kernel") == 6
+        sim.set_option("graph_steps", 64)                   # asking for a launch mode switches it off
+        assert sim.get_option("kernel") != 6
+    ob = np.zeros((256, 256), np.int32)
+    with pkg.Simulation(256, 256, DENSITY, ACCEL, OMEGA, ob, device=0) as sim:   # 2 x 72 B x 4096 cells per CTA do not fit
+        assert sim.get_option("kernel") != 6
+    ob = np.zeros((120, 128), np.int32)                      # ny % 16 != 0
+    with pkg.Simulation(128, 120, DENSITY, ACCEL, OMEGA, ob, device=0) as sim:
+        assert sim.get_option("kernel") != 6
