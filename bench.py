@@ -258,10 +258,13 @@ def peak_hbm():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def kernel_source_hash() -> str:
-    """sha256 over the kernel sources: profiles/roofline_traffic.json records the hash its ncu captures were taken at."""
+def kernel_source_hash(kernel=None) -> str:
+    """sha256 over the sources of one kernel: profiles/roofline_traffic.json records the hash its ncu captures were
+    taken at.  Kernel 7 lives in lbm_stepsk.cuh (on top of the helpers in lbm_kernels.cuh), the others do not see it."""
     h = hashlib.sha256()
     for path in sorted(glob.glob(os.path.join(ROOT, "mpilattice-boltzmann_b200", "csrc", "*.cuh"))):
+        if os.path.basename(path) == "lbm_stepsk.cuh" and str(kernel) != "7":
+            continue
         h.update(os.path.basename(path).encode())
         h.update(open(path, "rb").read())
     return h.hexdigest()[:16]
@@ -277,7 +280,7 @@ def measured_traffic(nx, ny, kernel):
         top = json.load(open(path))
         rec = top.get("kernels", {}).get(str(kernel), top)
         measured_at = rec.get("source_hash", top.get("source_hash"))
-        now = kernel_source_hash()
+        now = kernel_source_hash(kernel)
         if measured_at != now:
             return None, f"ncu capture was taken at kernel sources {measured_at}, the sources are now {now}: re-capture"
         if rec["nx"] == nx and rec["ny"] == ny:
@@ -325,8 +328,9 @@ def bench_ours(args, pkg):
 
     nx, n = args.nx, world
     ips, K, W = args.timesteps, args.steps, args.warmup
-    tuning_keys = ("kernel", "graph_steps", "ctas_per_sm", "min_ctas", "fused2", "band_rows", "prefetch_rows", "cache_hint", "fused_deep")
-    pingpong_only = ("kernel", "min_ctas", "fused2", "band_rows", "prefetch_rows", "fused_deep")
+    tuning_keys = ("kernel", "graph_steps", "ctas_per_sm", "min_ctas", "fused2", "fused_steps", "band_rows", "prefetch_rows",
+                   "cache_hint", "fused_deep")
+    pingpong_only = ("kernel", "min_ctas", "fused2", "fused_steps", "band_rows", "prefetch_rows", "fused_deep")
 
     def make_sim(obstacles, fmt, rows, first, ny_global, ranks=n, inv=None):
         """One slab per rank on the CUDA IPC ring (ranks > 1) or the whole grid on this GPU, tuned as asked."""
@@ -368,8 +372,10 @@ def bench_ours(args, pkg):
     obstacles_t, obstacles = channel_bits(rows, first, ny_global)
     sim = make_sim(obstacles, "bits", rows, first, ny_global)
     kernel = sim.get_option("kernel")
+    fused_steps = sim.get_option("fused_steps") if kernel in (5, 7) else 1
     kernel_name = {1: "step_scalar", 2: "step_vec4", 3: "steps_resident", 4: "step_inplace",
-                   5: "steps2_strip (two timesteps per pass)"}.get(kernel, str(kernel))
+                   5: "steps2_strip (two timesteps per pass)",
+                   7: f"steps_strip<{fused_steps}> ({fused_steps} timesteps per pass)"}.get(kernel, str(kernel))
 
     # ---- parity: the same path, a small case, bit for bit, before anything is timed -------
     parity = {"checked": False, "reason": "--no-parity"}
@@ -384,7 +390,7 @@ def bench_ours(args, pkg):
             p_inv = float(pkg.decks.free_cells_inv(nx * p_ny - int(p_ob.sum())))
             psim = make_sim(np.ascontiguousarray(p_ob[p_first:p_first + par.ROWS_PER_RANK]), "int32", par.ROWS_PER_RANK,
                             p_first, p_ny, inv=p_inv)
-            if kernel == 5:
+            if kernel in (5, 7):
                 psim.set_option("fused2", 1)             # the timed kernel (automatic only from 2^22 cells per GPU)
                 if distributed:
                     dist.barrier()                       # every rank has switched before any rank runs
@@ -452,8 +458,9 @@ def bench_ours(args, pkg):
     cells_global = float(nx) * ny_global
     timesteps = K * ips
     value = cells_global * timesteps / (device_ms * 1e-3) / 1e6
-    # the dominant kernel: one launch per timestep, or (kernel 5, "fused2") one per PAIR of timesteps
-    steps_per_launch = 2 if kernel == 5 else 1
+    # the dominant kernel: one launch per timestep, or (kernels 5 and 7) one per 2..4 timesteps; the few shorter
+    # passes that finish a 256-step chunk are averaged in
+    steps_per_launch = fused_steps
     step_launches = timesteps // steps_per_launch
     launch_ms = device_ms * steps_per_launch / timesteps
     peak, peak_src = peak_hbm()
@@ -555,10 +562,10 @@ def bench_ours(args, pkg):
                          "what": (f"{kernel_name}, {BYTES_PER_CELL_STEP:.0f} B/cell/step x {steps_per_launch} timestep(s) x "
                                   f"{nx * rows} cells per launch per GPU, mean launch {launch_ms * 1e3:.1f} us over "
                                   f"{step_launches} launches"
-                                  + ("; two timesteps are fused per pass over HBM, so the DRAM traffic per launch (`traffic`) is "
-                                     "about half the algorithmic bytes and `frac` exceeds the one-step streaming roofline; "
-                                     "`dram_frac` = traffic / launch time / peak is the share of the HBM roof actually used"
-                                     if kernel == 5 else "")),
+                                  + (f"; {fused_steps} timesteps are fused per pass over HBM, so the DRAM traffic per launch "
+                                     f"(`traffic`) is about 1/{fused_steps} of the algorithmic bytes and `frac` exceeds the one-step "
+                                     "streaming roofline; `dram_frac` = traffic / launch time / peak is the share of the HBM "
+                                     "roof actually used" if kernel in (5, 7) else "")),
                          "dram_gbs": round(traffic / (launch_ms * 1e-3) / 1e9, 1) if traffic else None,
                          "dram_frac": round(traffic / (launch_ms * 1e-3) / 1e9 / peak, 4) if traffic else None},
             "clocks": clocks,
@@ -591,6 +598,8 @@ def main():
     ap.add_argument("--min-ctas", dest="min_ctas", type=int, default=None)
     ap.add_argument("--fused2", type=int, default=None, choices=[-1, 0, 1],
                     help="two timesteps per pass over HBM: 1 on, 0 off, default automatic (on from 2^22 cells per GPU)")
+    ap.add_argument("--fused-steps", dest="fused_steps", type=int, default=None, choices=[2, 3, 4],
+                    help="timesteps per pass over HBM of the fused kernel (2 = kernel 5, 3 or 4 = kernel 7)")
     ap.add_argument("--band-rows", dest="band_rows", type=int, default=None)
     ap.add_argument("--prefetch-rows", dest="prefetch_rows", type=int, default=None, help="kernel 5: L2 prefetch distance in rows")
     ap.add_argument("--cache-hint", dest="cache_hint", type=int, default=None)

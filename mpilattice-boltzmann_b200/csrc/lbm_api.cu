@@ -21,6 +21,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
+#include "lbm_stepsk.cuh"
 
 namespace {
 
@@ -82,6 +83,7 @@ struct Slab {
   int threads_int = 256, grid_int = 0;
   int per_step = 1;
   int fused_grid = 0, fused_bands = 0, fused_band_rows = 0;   // two-steps-per-pass kernel (kernel 5)
+  unsigned fusedk_attr = 0;              // kernel 7: bit 2K+D set once steps_strip<K, D> has its shared-memory opt-in on this device
   bool fused_attr = false;              // its dynamic shared memory opt-in has been made on this slab's device
   std::vector<cudaGraphExec_t> graphs;  // [parity]
 };
@@ -124,12 +126,14 @@ struct lbm_b200 {
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
   long opt_cluster = -1;                // kernel 6: -1 automatic, 0 never, 1 wherever it fits
+  long opt_fused_steps = 2;             // timesteps per pass over HBM of the fused kernel: 2 = kernel 5, 3 or 4 = kernel 7
   long opt_fused_deep = 1;              // kernel 5: two staging rows, 3 CTAs x 4 warps per SM (+3 %, profiles/r02_fused2.md)
   long opt_prefetch_rows = 0;           // kernel 5: L2 prefetch distance in rows (0 = off: measured slower, profiles/r02_fused2.md)
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
   long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
   bool failed = false;                  // a wait timed out: the state is garbage, only destroy is valid
-  bool fused2 = false;                  // two timesteps per pass over HBM (kernel 5) are in use
+  bool fused2 = false;                  // two (or more) timesteps per pass over HBM (kernel 5 / 7) are in use
+  int fusedk = 0;                       // kernel 7 is in use with this many timesteps per pass (0 = kernel 5)
   int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   bool cluster = false;                 // the grid lives in the shared memory of one 16-CTA cluster (kernel 6)
@@ -268,12 +272,74 @@ bool want_fused2(const lbm_b200* h)
 constexpr int fused_warps(bool deep) { return deep ? 4 : 8; }
 constexpr size_t fused_smem(bool deep) { return (size_t)fused_warps(deep) * lbm::fused_warp_float4(deep) * sizeof(float4); }
 
+// Launch shape of kernel 7 for k steps per pass and d staging rows: warps per CTA x CTAs per SM = the warps whose
+// rings and staging rows fit into an SM's shared memory (lbm::stepsk_max_warps).
+void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm)
+{
+  auto max_warps = [&]() {
+    switch (k * 10 + d) {
+      case 11: return lbm::stepsk_max_warps(1, 1); case 12: return lbm::stepsk_max_warps(1, 2);
+      case 21: return lbm::stepsk_max_warps(2, 1); case 22: return lbm::stepsk_max_warps(2, 2);
+      case 31: return lbm::stepsk_max_warps(3, 1); case 32: return lbm::stepsk_max_warps(3, 2);
+      case 41: return lbm::stepsk_max_warps(4, 1); default: return lbm::stepsk_max_warps(4, 2);
+    }
+  };
+  const int w = max_warps();
+  int ctas = 1;
+  for (int c : {3, 2}) if (w % c == 0) { ctas = c; break; }   // small CTAs where the count divides: finer scheduling
+  *ctas_per_sm = ctas;
+  *warps_per_cta = w / ctas;
+}
+
+// Kernel 7 (K = 3 or 4 timesteps per pass) where kernel 5 applies, K was asked for and the rows allow it.
+bool want_fusedk(const lbm_b200* h)
+{
+  if (h->opt_fused_steps < 3) return false;
+  if (h->n_ranks > 1) return false;
+  return h->ny >= 2 * lbm::kHalo;
+}
+
+// Band plan of the fused kernels for k timesteps per pass (lbm_b200_plan_bands is the k = 2 case): every work item
+// recomputes 2(k-1) rows (+ half a row of start-up), one item per resident warp at a time.
+// `warps_per_sm` = resident warps (= work items in flight) per multiprocessor of the kernel variant in use.
+void plan_bands_k(int rows, int nx, int band_rows, int sms, int k, int warps_per_sm, bool ring, int* bands_out, int* rows_per_band)
+{
+  const int strips = (nx + lbm::kStripOut - 1) / lbm::kStripOut;
+  const int min_edge = (k <= 2) ? 2 : (ring ? lbm::kHalo : 1);     // rows the first and the last band must hold
+  int want = band_rows;
+  if (want <= 0) {
+    const long slots = (long)sms * warps_per_sm;
+    double best = 0;
+    for (int b : {8, 12, 16, 24, 32, 48, 64, 96, 128, 192, 256}) {
+      if (k <= 2 && b > 128) break;
+      const int nb = (rows + b - 1) / b;
+      const int per_b = (rows + nb - 1) / nb;
+      // Fitted to the band sweeps of profiles/r02_fused2.md (2048^2, 4096^2, 16384 x 2048, 16384^2): the items run
+      // `fill` deep on every resident warp; CTAs are handed out as others finish, so a launch costs its work plus a
+      // ragged end of ~0.6 item; a launch whose items all fit at once runs every warp in the same phase (1.37 x
+      // slower per row than the steady state) and no faster than a warp alone can go (0.63 of a full SM's pace).
+      const double fill = (double)nb * strips / (double)slots;
+      const double cost = (per_b + 2.0 * (k - 1) + 0.5) * (fill > 1.0 ? fill + 0.62 : 1.37 * std::max(0.63, fill));
+      if (want <= 0 || cost < best) { best = cost; want = b; }
+    }
+  }
+  int bands = std::max(1, (rows + want - 1) / want);
+  int per = (rows + bands - 1) / bands;
+  while (bands > 1 && (per < min_edge || rows - (bands - 1) * per < min_edge)) {
+    bands--;
+    per = (rows + bands - 1) / bands;
+  }
+  *bands_out = bands;
+  *rows_per_band = per;
+}
+
 void plan(lbm_b200* h)
 {
   h->resident = want_resident(h);
   h->fused2 = want_fused2(h);
   h->cluster = !(h->fused2 && h->opt_fused2 == 1) && want_cluster(h);
   if (h->cluster) h->resident = h->fused2 = false;
+  h->fusedk = (h->fused2 && want_fusedk(h)) ? (int)h->opt_fused_steps : 0;
   if (h->fused2) {
     h->resident = false;
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
@@ -281,11 +347,14 @@ void plan(lbm_b200* h)
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
       int bands = 1, per = s.rows;
-      lbm_b200_plan_bands(s.rows, h->nx, (int)h->opt_band_rows, sms, &bands, &per);
+      int k7_wpc = 0, k7_ctas = 0;
+      if (h->fusedk) stepsk_shape(h->fusedk, h->opt_fused_deep != 0 ? 2 : 1, &k7_wpc, &k7_ctas);
+      const int resident_warps = h->fusedk ? k7_wpc * k7_ctas : (h->opt_fused_deep != 0 ? 12 : 16);
+      plan_bands_k(s.rows, h->nx, (int)h->opt_band_rows, sms, h->fusedk ? h->fusedk : 2, resident_warps, h->n_ranks > 1, &bands, &per);
       s.fused_bands = bands;
       s.fused_band_rows = per;
       const long items = (long)h->fused_strips * bands;
-      const int wpc = fused_warps(h->opt_fused_deep != 0);
+      const int wpc = h->fusedk ? k7_wpc : fused_warps(h->opt_fused_deep != 0);
       s.fused_grid = (int)std::min<long>((items + wpc - 1) / wpc, 1L << 30);
       if (h->opt_ctas_per_sm > 0) {
         int sms = 148;
@@ -742,6 +811,67 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
   return LBM_B200_OK;
 }
 
+// K' <= K timesteps in one pass over HBM (kernel 7): partial slots `slot` .. `slot`+K'-1.  Shorter passes finish a
+// chunk or a run through the same strips (and, on a ring, the same handshake and halo depth).
+template <int K, int D>
+int launch_stepsk(lbm_b200* h, Slab& s, const StepArgs& a, const lbm::StepsKArgs& g)
+{
+  int wpc = 0, ctas = 0;
+  stepsk_shape(K, D, &wpc, &ctas);
+  const size_t smem = (size_t)wpc * lbm::stepsk_warp_bytes(K, D);
+  auto kernel = lbm::steps_strip<K, D, 0, false>;
+  const unsigned bit = 1u << (2 * K + D);
+  if (!(s.fusedk_attr & bit)) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    s.fusedk_attr |= bit;
+  }
+  const long items = (long)g.bands * g.strips;
+  long grid = (items + wpc - 1) / wpc;
+  if (h->opt_ctas_per_sm > 0) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+    grid = std::min<long>(grid, (long)sms * h->opt_ctas_per_sm);
+  }
+  grid = std::min<long>(grid, s.per_step);                   // one partial per CTA and step
+  kernel<<<dim3((unsigned)grid), dim3(wpc * 32), smem, s.stream>>>(a, g);
+  CUDA_TRY(cudaGetLastError());
+  return LBM_B200_OK;
+}
+
+int enqueue_fusedk(lbm_b200* h, int slot, int k, bool fold_last)
+{
+  for (Slab& s : h->slabs) {
+    if (&s - h->slabs.data() == h->opt_debug_skip_slab) continue;
+    CUDA_TRY(cudaSetDevice(s.device));
+    StepArgs a = base_args(h, s, slot, false);
+    a.row_begin = 1; a.row_count = s.rows; a.row_stride = 1;
+    a.south_of_first = s.rows;
+    a.north_of_last = 1;
+    lbm::StepsKArgs g{};
+    g.band_rows = s.fused_band_rows;
+    g.bands = s.fused_bands;
+    g.strips = h->fused_strips;
+    g.accel_y = s.accel_row >= 1 ? s.accel_row - 1 : -1000;
+    g.fold_last = fold_last ? 1 : 0;
+    g.partial_stride = s.per_step;
+    int rc;
+    switch (k * 10 + (h->opt_fused_deep != 0 ? 2 : 1)) {
+      case 11: rc = launch_stepsk<1, 1>(h, s, a, g); break;
+      case 12: rc = launch_stepsk<1, 2>(h, s, a, g); break;
+      case 21: rc = launch_stepsk<2, 1>(h, s, a, g); break;
+      case 22: rc = launch_stepsk<2, 2>(h, s, a, g); break;
+      case 31: rc = launch_stepsk<3, 1>(h, s, a, g); break;
+      case 32: rc = launch_stepsk<3, 2>(h, s, a, g); break;
+      case 41: rc = launch_stepsk<4, 1>(h, s, a, g); break;
+      default: rc = launch_stepsk<4, 2>(h, s, a, g); break;
+    }
+    if (rc) return rc;
+    h->launches++;
+  }
+  h->cur ^= 1;
+  return LBM_B200_OK;
+}
+
 int enqueue_reduce(lbm_b200* h, int steps)
 {
   for (Slab& s : h->slabs) {
@@ -887,6 +1017,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
   if (const char* e = getenv("LBM_B200_CLUSTER")) h->opt_cluster = std::max(-1L, std::min(1L, atol(e)));
+  if (const char* e = getenv("LBM_B200_FUSED_STEPS")) h->opt_fused_steps = std::max(2L, std::min((long)lbm::kHalo, atol(e)));
   if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = atol(e) != 0;
   if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
 }
@@ -957,32 +1088,11 @@ int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands_out
 {
   if (rows < 2 || nx < 4 || sms < 1 || band_rows < 0 || !bands_out || !rows_per_band)
     return fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_plan_bands");
-  const int strips = (nx + lbm::kStripOut - 1) / lbm::kStripOut;
   // Automatic height: every work item recomputes two rows, and the items run in waves of one per resident warp
-  // (2 CTAs x 8 warps per SM) -- take the height with the cheapest waves x (rows + 2.5); reproduces the measured
-  // optima (16 at 2048^2, 64 at 4096^2 and 16384^2, profiles/r01_fused2.md).
-  int want = band_rows;
-  if (want <= 0) {
-    const long slots = (long)sms * 16;
-    double best = 0;
-    for (int b : {8, 12, 16, 24, 32, 48, 64, 96, 128}) {
-      const int nb = (rows + b - 1) / b;
-      const int per_b = (rows + nb - 1) / nb;
-      const long waves = ((long)nb * strips + slots - 1) / slots;
-      const double cost = (double)waves * (per_b + 2.5);
-      if (want <= 0 || cost < best) { best = cost; want = b; }
-    }
-  }
-  // balanced bands; the first and the last one hold at least two rows (a ring slab pushes two rows per direction
-  // and publishes them from one work item)
-  int bands = std::max(1, (rows + want - 1) / want);
-  int per = (rows + bands - 1) / bands;
-  while (bands > 1 && (per < 2 || rows - (bands - 1) * per < 2)) {
-    bands--;
-    per = (rows + bands - 1) / bands;
-  }
-  *bands_out = bands;
-  *rows_per_band = per;
+  // (kernel 5's default shape: 3 CTAs x 4 warps per SM) -- take the height with the cheapest waves x (rows + 2.5).
+  // Balanced bands; the first and the last one hold at least two rows (a ring slab pushes two rows per direction
+  // and publishes them from one work item).
+  plan_bands_k(rows, nx, band_rows, sms, 2, 12, false, bands_out, rows_per_band);
   return LBM_B200_OK;
 }
 
@@ -1413,7 +1523,11 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       }
       for (int i = 0; i < n; i++) {
         int rc;
-        if (h->fused2 && i + 1 < n) {                  // steps t+i and t+i+1 in one pass over HBM
+        if (h->fusedk) {                               // up to K steps from t+i on in one pass over HBM
+          const int k = std::min(h->fusedk, n - i);
+          rc = enqueue_fusedk(h, i, k, t + i + k - 1 != iters - 1);
+          i += k - 1;
+        } else if (h->fused2 && i + 1 < n) {           // steps t+i and t+i+1 in one pass over HBM
           rc = enqueue_fused2(h, i, t + i + 1 != iters - 1, false);
           i++;
         } else if (h->fused2 && h->n_ranks > 1) {      // a ring's odd step: same strips, same handshake
@@ -1665,6 +1779,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "cluster")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster must be -1, 0 or 1");
     h->opt_cluster = value;
+  } else if (!strcmp(key, "fused_steps")) {
+    if (value < 2 || value > lbm::kHalo) return fail(LBM_B200_ERR_ARG, "fused_steps must be 2, 3 or 4");
+    h->opt_fused_steps = value;
   } else if (!strcmp(key, "band_rows")) {
     if (value < 0 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 0 (automatic) .. 2^20");
     h->opt_band_rows = value;
@@ -1708,7 +1825,8 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
 int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
 {
   if (!h || !key || !value) return fail(LBM_B200_ERR_ARG, "NULL argument");
-  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->cluster ? 6 : (h->fused2 ? 5 : (h->resident ? 3 : (use_vec4(h) ? 2 : 1))));
+  if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->cluster ? 6 : (h->fused2 ? (h->fusedk ? 7 : 5) : (h->resident ? 3 : (use_vec4(h) ? 2 : 1))));
+  else if (!strcmp(key, "fused_steps")) *value = h->fused2 ? (h->fusedk ? h->fusedk : 2) : 1;
   else if (!strcmp(key, "cluster")) *value = h->cluster ? 1 : 0;
   else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;

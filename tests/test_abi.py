@@ -92,8 +92,8 @@ def test_bad_arguments_are_rejected_before_any_device_work(pkg):
 
 def test_band_plan_of_the_fused_kernel(pkg):
     """Every row belongs to exactly one band, all bands but the last are equally tall, the first and the last hold
-    at least two rows (ring slabs push two rows per direction from one work item); the automatic height reproduces the
-    measured optima."""
+    at least two rows (ring slabs push two rows per direction from one work item); the automatic height stays inside
+    the measured optima."""
     lib = pkg.library()
 
     def plan(rows, nx, want, sms=148):
@@ -108,8 +108,10 @@ def test_band_plan_of_the_fused_kernel(pkg):
             assert bands >= 1 and per >= 1 and 0 < last <= max(per, rows)
             if bands > 1:
                 assert per >= 2 and last >= 2, (rows, want, bands, per)
-    assert plan(2048, 2048, 0)[1] == 16 and plan(4096, 4096, 0)[1] == 64
-    assert plan(16384, 16384, 0)[1] in (64, 96)
+    # measured optima of the 12-warps-per-SM kernel (profiles/r02_fused2.md): 24..32 at 2048^2, 12..24 at 4096^2,
+    # 32..64 at 16384^2 and on the 2048-row slabs of an eight-way split of 16384^2 (128 is 15 % slower there)
+    assert plan(2048, 2048, 0)[1] in (24, 32) and plan(4096, 4096, 0)[1] in (12, 16, 24)
+    assert plan(16384, 16384, 0)[1] in (32, 64) and plan(2048, 16384, 0)[1] in (16, 32, 64)
     assert lib.lbm_b200_plan_bands(1, 1024, 0, 148, None, None) != 0
 
 

@@ -183,3 +183,28 @@ def test_cluster_kernel_is_the_default_for_the_small_decks_only(pkg):
     ob = np.zeros((120, 128), np.int32)                      # ny % 16 != 0
     with pkg.Simulation(128, 120, DENSITY, ACCEL, OMEGA, ob, device=0) as sim:
         assert sim.get_option("kernel") != 6
+
+
+@pytest.mark.parametrize("steps,stage_rows", [(3, 1), (3, 2), (4, 1), (4, 2)])
+@pytest.mark.parametrize("shape,band", [((500, 77), 0), ((500, 77), 5), ((240, 9), 0), ((1024, 40), 7), ((368, 130), 64)])
+def test_k_steps_per_pass_kernel_is_bit_identical(pkg, oracle, steps, stage_rows, shape, band):
+    """Kernel 7 (three / four timesteps per pass over HBM): random obstacles on every edge (x- and y-wrap), an
+    arbitrary initial state, ragged last strip and band, run lengths that leave every possible shorter last pass
+    (K' = 1 .. K-1), back-to-back runs, and a run longer than one 256-step chunk."""
+    nx, ny = shape
+    rng = np.random.default_rng(nx + ny + steps)
+    obstacles = random_obstacles(rng, ny, nx, 0.05, walls=False)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    runs = (1, 2, 3, 4, 5, 7, 260) if shape == (500, 77) and band == 0 else (7, 6, 1, 12)
+    ref_av = oracle.run(ref, obstacles, sum(runs), DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+        sim.set_option("fused2", 1)
+        sim.set_option("fused_steps", steps)
+        sim.set_option("fused_deep", stage_rows - 1)       # one or two staging rows (copies one / two rows ahead)
+        sim.set_option("band_rows", band)
+        assert sim.get_option("kernel") == 7 and sim.get_option("fused_steps") == steps
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(n) for n in runs])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4

@@ -2,7 +2,7 @@
 """Records the DRAM bytes per launch of one kernel from an `ncu --set full` capture in profiles/roofline_traffic.json.
 
     ncu -i X.ncu-rep --page raw --csv > X_raw.csv
-    tools/ncu_to_traffic.py X_raw.csv <kernel number: 2 | 4 | 5> <nx> <ny> "<what was captured>"
+    tools/ncu_to_traffic.py X_raw.csv <kernel number: 2 | 4 | 5 | 7> <nx> <ny> "<what was captured>" [timesteps per launch]
 
 bench.py reads the record for `roofline.traffic`; the record carries the hash of the kernel sources the capture was
 taken on (bench.kernel_source_hash), so a capture of older kernels is never quoted for newer ones.
@@ -29,11 +29,11 @@ def main():
         return float(first[i]) * UNIT[units[i]]
 
     rd, wr = metric("dram__bytes_read.sum"), metric("dram__bytes_write.sum")
-    steps = 2 if kernel == "5" else 1
+    steps = int(sys.argv[6]) if len(sys.argv) > 6 else (2 if kernel == "5" else 1)
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     top = json.load(open(path)) if os.path.exists(path) else {}
     top.setdefault("kernels", {})[kernel] = {
-        "capture": what, "kernel_name": first[hdr.index("Kernel Name")], "source_hash": kernel_source_hash(),
+        "capture": what, "kernel_name": first[hdr.index("Kernel Name")], "source_hash": kernel_source_hash(kernel),
         "nx": nx, "ny": ny, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
         "dram_bytes_per_cell_per_step": (rd + wr) / (nx * ny) / steps,
         "algorithmic_bytes_per_launch": 72 * steps * nx * ny,
