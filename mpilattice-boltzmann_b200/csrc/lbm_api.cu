@@ -137,6 +137,8 @@ struct lbm_b200 {
   int fused_strips = 0;
   bool resident = false;                // the cooperative many-steps-per-launch kernel is in use
   bool cluster = false;                 // the grid lives in the shared memory of one 16-CTA cluster (kernel 6)
+  bool cluster_rows = false;            // ... in its one-warp-per-row form (nx = 128, kernel 6b)
+  long opt_cluster_rows = 1;            // 0 = always the general form of kernel 6 (tests, A/B)
   int cluster_threads = 0;
   int last_iters = 0;
   int graph_len = 0;
@@ -215,7 +217,13 @@ bool want_resident(const lbm_b200* h)
 }
 
 // Kernel 6: single-GPU ping-pong handles whose grid fits twice into the shared memory of one 16-CTA cluster.
-size_t cluster_smem_bytes(const lbm_b200* h) { return 2 * 9 * sizeof(float) * (size_t)(h->ny / lbm::kClusterCtas) * h->nx; }
+// (the one-warp-per-row form, kernel 6b, keeps two halo rows per CTA as well)
+size_t cluster_smem_bytes(const lbm_b200* h)
+{
+  const size_t rows = (size_t)(h->ny / lbm::kClusterCtas);
+  if (!h->cluster_rows) return 2 * 9 * sizeof(float) * rows * h->nx;
+  return 2 * 9 * sizeof(float) * (rows + 2) * h->nx + (size_t)kChunkSteps * rows * sizeof(double);   // + the steps' sums
+}
 
 bool want_cluster(lbm_b200* h)
 {
@@ -223,6 +231,8 @@ bool want_cluster(lbm_b200* h)
   // automatic: only where the caller has not asked for a particular kernel / launch mode
   if (h->opt_cluster < 0 && (h->opt_kernel != 0 || h->opt_resident == 1 || h->opt_graph_steps >= 0 || h->opt_fused2 == 1)) return false;
   if (h->ny % lbm::kClusterCtas != 0 || h->ny / lbm::kClusterCtas < 1) return false;
+  // 128 cells wide (the two smallest shipped decks): one warp per row for the whole launch
+  h->cluster_rows = h->nx == lbm::kClusterRowCells && h->ny / lbm::kClusterCtas <= lbm::kClusterMaxRows && h->opt_cluster_rows != 0;
   const size_t bytes = cluster_smem_bytes(h);
   int max_smem = 0, cluster_ok = 0;
   const int dev = h->slabs[0].device;
@@ -230,11 +240,13 @@ bool want_cluster(lbm_b200* h)
   cudaDeviceGetAttribute(&cluster_ok, cudaDevAttrClusterLaunch, dev);
   if (!cluster_ok || bytes > (size_t)max_smem) return false;
   const int ncell = (h->ny / lbm::kClusterCtas) * h->nx;
-  h->cluster_threads = std::min(1024, (ncell + 31) / 32 * 32);
+  h->cluster_threads = h->cluster_rows ? 32 * (h->ny / lbm::kClusterCtas) : std::min(1024, (ncell + 31) / 32 * 32);
   // can one cluster of 16 such CTAs be resident?  (non-portable cluster size: opt in first)
   cudaSetDevice(dev);
-  if (cudaFuncSetAttribute(lbm::steps_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-      cudaFuncSetAttribute(lbm::steps_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+  void (*const kernel)(lbm::ClusterArgs) = !h->cluster_rows ? lbm::steps_cluster
+      : (h->ny / lbm::kClusterCtas <= 8 ? lbm::steps_cluster_rows<8> : lbm::steps_cluster_rows<lbm::kClusterMaxRows>);
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
@@ -245,7 +257,7 @@ bool want_cluster(lbm_b200* h)
   attr.val.clusterDim.x = lbm::kClusterCtas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   int clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&clusters, lbm::steps_cluster, &cfg) != cudaSuccess || clusters < 1) {
+  if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess || clusters < 1) {
     cudaGetLastError();
     return false;
   }
@@ -291,12 +303,31 @@ void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm)
   *warps_per_cta = w / ctas;
 }
 
+// Padded rows of a plane beyond the slab's own: lbm::kHalo halo rows per side.  Rows 0 and rows+1 are the ones next to
+// the slab (all ring kernels), rows+2(d-1) / rows+2(d-1)+1 the southern / northern neighbour's row d rows away (d = 2
+// for kernel 5, d = 2..4 for kernel 7).  The obstacle words of the neighbours' rows follow the slab's own in the same
+// order: word row rows+2(d-1) = the southern neighbour's d-th row from its end, rows+2(d-1)+1 = the northern
+// neighbour's d-th row.
+constexpr int kPad = 2 * lbm::kHalo;
+// 0-based row (negative / >= rows: a neighbour's) that padded row r holds
+int y_of_padded(int rows, int r)
+{
+  if (r <= rows + 1) return r - 1;
+  const int d = (r - rows) / 2 + 1;
+  return ((r - rows) % 2 == 0) ? -d : rows - 1 + d;
+}
+
 // Kernel 7 (K = 3 or 4 timesteps per pass) where kernel 5 applies, K was asked for and the rows allow it.
 bool want_fusedk(const lbm_b200* h)
 {
   if (h->opt_fused_steps < 3) return false;
-  if (h->n_ranks > 1) return false;
-  return h->ny >= 2 * lbm::kHalo;
+  if (h->n_ranks == 1) return h->ny >= 2 * lbm::kHalo;
+  // a ring: every slab holds its neighbours' kHalo rows, and the driven row ny-2 must not be a row a slab other than
+  // the one north of its owner recomputes (a whole-domain handle sees all slabs, a one-slab-per-process handle its
+  // own and -- once connected -- its neighbours': lbm_b200_enqueue refuses to run on thinner ones)
+  for (const Slab& s : h->slabs)
+    if (s.rows < lbm::kHalo + 2) return false;
+  return h->ny / h->n_ranks >= lbm::kHalo + 2;
 }
 
 // Band plan of the fused kernels for k timesteps per pass (lbm_b200_plan_bands is the k = 2 case): every work item
@@ -452,11 +483,11 @@ int alloc_slab(lbm_b200* h, Slab& s, const void* obstacles_rows, int format)
   const bool trace = getenv("LBM_B200_TRACE") != nullptr;
   const double t0 = now_s();
   CUDA_TRY(cudaSetDevice(s.device));
-  if ((unsigned long long)(s.rows + 4) * (unsigned long long)h->nx >= (1ull << 32))
+  if ((unsigned long long)(s.rows + kPad) * (unsigned long long)h->nx >= (1ull << 32))
     return fail(LBM_B200_ERR_ARG, "a slab of %d x %d cells is too large: offsets inside a plane are 32-bit (use more slabs)", h->nx, s.rows);
-  // padded rows: 0 and rows+1 are the halo rows next to the slab, rows+2 / rows+3 the second halo rows (the
-  // southern / northern neighbour's row one further away; used by the two-steps-per-pass kernel on a ring)
-  s.plane = (size_t)(s.rows + 4) * h->nx;
+  // padded rows: 0 and rows+1 are the halo rows next to the slab, the rest the neighbours' rows further away that
+  // the fused kernels keep on a ring (see kPad)
+  s.plane = (size_t)(s.rows + kPad) * h->nx;
   const size_t bytes = 9 * s.plane * sizeof(float);
   for (int b = 0; b < (h->inplace ? 1 : 2); b++) {
     cudaError_t e = cudaMalloc(&s.buf[b], bytes);
@@ -477,8 +508,8 @@ int alloc_slab(lbm_b200* h, Slab& s, const void* obstacles_rows, int format)
   // obstacle rows: the reference's int-per-cell array (or one byte per cell) is uploaded into the (still unused)
   // second population buffer and bit-packed on the device -- 32 cells per word, rows padded to whole words; rows
   // that arrive bit-packed go straight into place
-  // (three more rows of words follow the slab's own: the neighbours' rows -1, `rows` and -2, see set_halo_mask)
-  const size_t words = (size_t)(s.rows + 3) * h->mask_row_words;
+  // (the words of the neighbours' rows follow the slab's own, see kPad and set_halo_mask)
+  const size_t words = (size_t)(s.rows + kPad) * h->mask_row_words;
   CUDA_TRY(cudaMalloc(&s.mask, std::max<size_t>(words, 1) * sizeof(uint32_t)));
   CUDA_TRY(cudaMemsetAsync(s.mask, 0, std::max<size_t>(words, 1) * sizeof(uint32_t), s.stream));
   CUDA_TRY(cudaMalloc(&s.blocked_dev, sizeof(unsigned long long)));
@@ -506,19 +537,17 @@ int alloc_slab(lbm_b200* h, Slab& s, const void* obstacles_rows, int format)
   return LBM_B200_OK;
 }
 
-// Obstacle words of the three neighbour rows a ring slab computes redundantly in the two-steps-per-pass kernel:
-// word row `rows` = the southern neighbour's last row (y = -1), rows+1 = the northern neighbour's first row
-// (y = rows), rows+2 = the southern neighbour's second-to-last row (y = -2, only for the body-force pre-pass).
-int set_halo_mask(lbm_b200* h, Slab& s, const void* row_m1, const void* row_p, const void* row_m2, int format)
+// Obstacle words of the neighbours' rows a ring slab computes redundantly in the fused kernels (and of row -2 for
+// the body-force pre-pass): rows_src[j] = the obstacle row that goes into word row rows + j (see kPad).
+int set_halo_mask(lbm_b200* h, Slab& s, const void* const (&rows_src)[kPad], int format)
 {
   CUDA_TRY(cudaSetDevice(s.device));
   const size_t row_bytes = obstacle_row_bytes(h, format);
   char* staged = nullptr;
-  CUDA_TRY(cudaMalloc(&staged, 3 * row_bytes));
-  const void* src[3] = {row_m1, row_p, row_m2};
+  CUDA_TRY(cudaMalloc(&staged, kPad * row_bytes));
   int rc = LBM_B200_OK;
-  for (int i = 0; i < 3 && rc == LBM_B200_OK; i++)
-    rc = upload_mask(h, s, src[i], format, 1, staged + (size_t)i * row_bytes, s.mask + (size_t)(s.rows + i) * h->mask_row_words, nullptr);
+  for (int i = 0; i < kPad && rc == LBM_B200_OK; i++)
+    rc = upload_mask(h, s, rows_src[i], format, 1, staged + (size_t)i * row_bytes, s.mask + (size_t)(s.rows + i) * h->mask_row_words, nullptr);
   cudaError_t e = cudaStreamSynchronize(s.stream);
   cudaFree(staged);
   if (rc) return rc;
@@ -813,14 +842,14 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
 
 // K' <= K timesteps in one pass over HBM (kernel 7): partial slots `slot` .. `slot`+K'-1.  Shorter passes finish a
 // chunk or a run through the same strips (and, on a ring, the same handshake and halo depth).
-template <int K, int D>
+template <int K, int D, bool PEER>
 int launch_stepsk(lbm_b200* h, Slab& s, const StepArgs& a, const lbm::StepsKArgs& g)
 {
   int wpc = 0, ctas = 0;
   stepsk_shape(K, D, &wpc, &ctas);
   const size_t smem = (size_t)wpc * lbm::stepsk_warp_bytes(K, D);
-  auto kernel = lbm::steps_strip<K, D, 0, false>;
-  const unsigned bit = 1u << (2 * K + D);
+  auto kernel = lbm::steps_strip<K, D, 0, PEER>;
+  const unsigned bit = 1u << (2 * K + D + (PEER ? 16 : 0));
   if (!(s.fusedk_attr & bit)) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     s.fusedk_attr |= bit;
@@ -854,16 +883,37 @@ int enqueue_fusedk(lbm_b200* h, int slot, int k, bool fold_last)
     g.accel_y = s.accel_row >= 1 ? s.accel_row - 1 : -1000;
     g.fold_last = fold_last ? 1 : 0;
     g.partial_stride = s.per_step;
+    const bool peer = h->n_ranks > 1;
+    if (peer) {
+      peer_args(h, s, a);
+      const int strips = h->fused_strips;                    // one flag word per strip and direction, as kernel 5
+      a.wait_from_south = s.flags + kFlagWords;
+      a.wait_from_north = s.flags + kFlagWords + strips;
+      a.signal_north = s.north.flags + kFlagWords;
+      a.signal_south = s.south.flags + kFlagWords + strips;
+      g.south_rows = s.south.rows;
+      g.north_rows = s.north.rows;
+      // the slab north of the driven row's owner recomputes that row (its row -2) in the steps before the last
+      if (s.first_row == 0 && s.accel_row < 0) g.accel_y = -2;
+    }
     int rc;
-    switch (k * 10 + (h->opt_fused_deep != 0 ? 2 : 1)) {
-      case 11: rc = launch_stepsk<1, 1>(h, s, a, g); break;
-      case 12: rc = launch_stepsk<1, 2>(h, s, a, g); break;
-      case 21: rc = launch_stepsk<2, 1>(h, s, a, g); break;
-      case 22: rc = launch_stepsk<2, 2>(h, s, a, g); break;
-      case 31: rc = launch_stepsk<3, 1>(h, s, a, g); break;
-      case 32: rc = launch_stepsk<3, 2>(h, s, a, g); break;
-      case 41: rc = launch_stepsk<4, 1>(h, s, a, g); break;
-      default: rc = launch_stepsk<4, 2>(h, s, a, g); break;
+    switch ((peer ? 100 : 0) + k * 10 + (h->opt_fused_deep != 0 ? 2 : 1)) {
+      case 11: rc = launch_stepsk<1, 1, false>(h, s, a, g); break;
+      case 12: rc = launch_stepsk<1, 2, false>(h, s, a, g); break;
+      case 21: rc = launch_stepsk<2, 1, false>(h, s, a, g); break;
+      case 22: rc = launch_stepsk<2, 2, false>(h, s, a, g); break;
+      case 31: rc = launch_stepsk<3, 1, false>(h, s, a, g); break;
+      case 32: rc = launch_stepsk<3, 2, false>(h, s, a, g); break;
+      case 41: rc = launch_stepsk<4, 1, false>(h, s, a, g); break;
+      case 42: rc = launch_stepsk<4, 2, false>(h, s, a, g); break;
+      case 111: rc = launch_stepsk<1, 1, true>(h, s, a, g); break;
+      case 112: rc = launch_stepsk<1, 2, true>(h, s, a, g); break;
+      case 121: rc = launch_stepsk<2, 1, true>(h, s, a, g); break;
+      case 122: rc = launch_stepsk<2, 2, true>(h, s, a, g); break;
+      case 131: rc = launch_stepsk<3, 1, true>(h, s, a, g); break;
+      case 132: rc = launch_stepsk<3, 2, true>(h, s, a, g); break;
+      case 141: rc = launch_stepsk<4, 1, true>(h, s, a, g); break;
+      default: rc = launch_stepsk<4, 2, true>(h, s, a, g); break;
     }
     if (rc) return rc;
     h->launches++;
@@ -954,8 +1004,9 @@ int resync_flags(lbm_b200* h)
 }
 
 // The one-step ring kernels keep only three planes of one halo row per side up to date; the two-steps-per-pass
-// kernel pulls from two full halo rows per side.  When it is switched on for a live ring, every slab fetches the
-// four rows from its neighbours' current buffers (all ranks idle: the caller's responsibility, as for set_cells).
+// kernels pull from two (kernel 5) or up to four (kernel 7) full halo rows per side.  When one is switched on for a
+// live ring, every slab fetches those rows from its neighbours' current buffers (all ranks idle: the caller's
+// responsibility, as for set_cells).
 int pull_halos(lbm_b200* h)
 {
   if (h->n_ranks == 1 || !h->connected || h->inplace) return LBM_B200_OK;
@@ -967,10 +1018,13 @@ int pull_halos(lbm_b200* h)
     float* me = s.buf[h->cur];
     for (int k = 0; k < 9; k++) {
       const size_t mk = (size_t)k * s.plane, sk = (size_t)k * s.south.plane, nk = (size_t)k * s.north.plane;
-      CUDA_TRY(cudaMemcpyAsync(me + mk, so + sk + (size_t)s.south.rows * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
-      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 2) * h->nx, so + sk + (size_t)(s.south.rows - 1) * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
-      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 1) * h->nx, no + nk + (size_t)1 * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
-      CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)(s.rows + 3) * h->nx, no + nk + (size_t)2 * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+      for (int d = 1; d <= lbm::kHalo; d++) {            // the neighbours' rows d rows away (padded rows: see kPad)
+        const int to_s = (d == 1) ? 0 : s.rows + 2 * (d - 1), to_n = (d == 1) ? s.rows + 1 : s.rows + 2 * (d - 1) + 1;
+        if (s.south.rows >= d)
+          CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)to_s * h->nx, so + sk + (size_t)(s.south.rows + 1 - d) * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+        if (s.north.rows >= d)
+          CUDA_TRY(cudaMemcpyAsync(me + mk + (size_t)to_n * h->nx, no + nk + (size_t)d * h->nx, row_bytes, cudaMemcpyDefault, s.stream));
+      }
     }
     CUDA_TRY(cudaStreamSynchronize(s.stream));
   }
@@ -1017,6 +1071,7 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_FUSED2")) h->opt_fused2 = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
   if (const char* e = getenv("LBM_B200_CLUSTER")) h->opt_cluster = std::max(-1L, std::min(1L, atol(e)));
+  if (const char* e = getenv("LBM_B200_CLUSTER_ROWS")) h->opt_cluster_rows = atol(e) != 0;
   if (const char* e = getenv("LBM_B200_FUSED_STEPS")) h->opt_fused_steps = std::max(2L, std::min((long)lbm::kHalo, atol(e)));
   if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = atol(e) != 0;
   if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
@@ -1171,8 +1226,13 @@ static int create_whole(lbm_b200** handle, int nx, int ny, float density, float 
   if (n_slabs > 1) {
     for (int i = 0; i < n_slabs; i++) {
       const int f = first[i], r = rows[i];
-      rc = set_halo_mask(h, h->slabs[i], ob + (size_t)((f - 1 + ny) % ny) * ob_row, ob + (size_t)((f + r) % ny) * ob_row,
-                         ob + (size_t)((f - 2 + 2 * ny) % ny) * ob_row, format);
+      const void* src[kPad];
+      for (int j = 0; j < kPad; j++) {
+        // word row rows+j holds the row of padded row rows+j, except the first two: rows -1 and `rows`
+        const int yy = (j == 0) ? -1 : (j == 1 ? r : y_of_padded(r, r + j));
+        src[j] = ob + (size_t)(((f + yy) % ny + ny) % ny) * ob_row;
+      }
+      rc = set_halo_mask(h, h->slabs[i], src, format);
       if (rc) { lbm_b200_destroy(h); return rc; }
     }
   }
@@ -1339,9 +1399,12 @@ static int connect_mapped(lbm_b200* h, Slab& s, const IpcBlob& sb, const IpcBlob
   }
   // obstacle words of the neighbours' rows this slab recomputes in the two-steps-per-pass kernel (set_halo_mask)
   const size_t w = (size_t)h->mask_row_words, bytes = w * sizeof(uint32_t);
-  CUDA_TRY(cudaMemcpy(s.mask + (size_t)s.rows * w, s.south.mask + (size_t)(s.south.rows - 1) * w, bytes, cudaMemcpyDefault));
-  CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 1) * w, s.north.mask, bytes, cudaMemcpyDefault));
-  CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2) * w, s.south.mask + (size_t)(s.south.rows - 2) * w, bytes, cudaMemcpyDefault));
+  for (int d = 1; d <= lbm::kHalo; d++) {
+    if (s.south.rows >= d)
+      CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2 * (d - 1)) * w, s.south.mask + (size_t)(s.south.rows - d) * w, bytes, cudaMemcpyDefault));
+    if (s.north.rows >= d)
+      CUDA_TRY(cudaMemcpy(s.mask + (size_t)(s.rows + 2 * (d - 1) + 1) * w, s.north.mask + (size_t)(d - 1) * w, bytes, cudaMemcpyDefault));
+  }
   return LBM_B200_OK;
 }
 
@@ -1356,7 +1419,7 @@ int lbm_b200_ipc_connect(lbm_b200* h, const void* south_blob, const void* north_
   memcpy(&nb, north_blob, sizeof nb);
   if ((sb.inplace != 0) != h->inplace || (nb.inplace != 0) != h->inplace)
     return fail(LBM_B200_ERR_ARG, "ring neighbours must all be in-place handles or all ping-pong handles");
-  if (sb.rows < 3 || nb.rows < 3 || sb.plane != (unsigned long long)(sb.rows + 4) * h->nx || nb.plane != (unsigned long long)(nb.rows + 4) * h->nx)
+  if (sb.rows < 3 || nb.rows < 3 || sb.plane != (unsigned long long)(sb.rows + kPad) * h->nx || nb.plane != (unsigned long long)(nb.rows + kPad) * h->nx)
     return fail(LBM_B200_ERR_ARG, "a neighbour's blob does not describe a slab of this grid (nx %d)", h->nx);
   CUDA_TRY(cudaSetDevice(s.device));
   const int rc = connect_mapped(h, s, sb, nb);
@@ -1382,6 +1445,12 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       if (s.rows < 4 || s.south.rows < 4 || s.north.rows < 4)
         return fail(LBM_B200_ERR_STATE, "the two-steps-per-pass kernel needs at least 4 rows in every slab of a ring (this slab %d, "
                     "south %d, north %d): set the option fused2 = 0 on every rank", s.rows, s.south.rows, s.north.rows);
+  if (h->fusedk && h->n_ranks > 1)
+    for (const Slab& s : h->slabs)
+      if (s.rows < lbm::kHalo + 2 || s.south.rows < lbm::kHalo + 2 || s.north.rows < lbm::kHalo + 2)
+        return fail(LBM_B200_ERR_STATE, "the %d-steps-per-pass kernel needs at least %d rows in every slab of a ring (this slab %d, "
+                    "south %d, north %d): set the option fused_steps = 2 on every rank", h->fusedk, lbm::kHalo + 2, s.rows,
+                    s.south.rows, s.north.rows);
   NvtxRange nvtx_range("lbm_b200 mainloop");
   h->last_iters = iters;
   h->launches = 0;
@@ -1471,7 +1540,9 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = lbm::kClusterCtas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, lbm::steps_cluster, ca));
+        if (!h->cluster_rows) CUDA_TRY(cudaLaunchKernelEx(&cfg, lbm::steps_cluster, ca));
+        else if (ca.rows_per_cta <= 8) CUDA_TRY(cudaLaunchKernelEx(&cfg, lbm::steps_cluster_rows<8>, ca));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, lbm::steps_cluster_rows<lbm::kClusterMaxRows>, ca));
         h->launches += 2;
         h->cur ^= 1;                                   // the state always lands in the other buffer
         int rc = enqueue_reduce(h, n);
@@ -1668,14 +1739,13 @@ int lbm_b200_set_cells(lbm_b200* h, const float* cells)
     CUDA_TRY(cudaSetDevice(s.device));
     float* scratch = nullptr;
     int step = 0;
-    int rc = staging(h, s, row_floats * sizeof(float), s.rows + 4, &scratch, &step);
+    int rc = staging(h, s, row_floats * sizeof(float), s.rows + kPad, &scratch, &step);
     if (rc) return rc;
-    // owned rows plus the halo rows (padded rows 0, rows+1 and the second halo rows rows+2 = row -2, rows+3 = row
-    // rows+1 of the slab), taken from the periodic global grid
-    for (int r0 = 0; r0 < s.rows + 4; r0 += step) {
-      const int n = std::min(step, s.rows + 4 - r0);
+    // owned rows plus all halo rows (see kPad), taken from the periodic global grid
+    for (int r0 = 0; r0 < s.rows + kPad; r0 += step) {
+      const int n = std::min(step, s.rows + kPad - r0);
       for (int r = r0; r < r0 + n; r++) {
-        const int y = (r <= s.rows + 1) ? r - 1 : (r == s.rows + 2 ? -2 : s.rows + 1);
+        const int y = y_of_padded(s.rows, r);
         const int gy = ((s.first_row + y) % h->ny + h->ny) % h->ny;
         CUDA_TRY(cudaMemcpyAsync(scratch + (size_t)(r - r0) * row_floats, cells + (size_t)gy * row_floats,
                                  row_floats * sizeof(float), cudaMemcpyHostToDevice, s.stream));
@@ -1779,6 +1849,9 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "cluster")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster must be -1, 0 or 1");
     h->opt_cluster = value;
+  } else if (!strcmp(key, "cluster_rows")) {
+    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster_rows must be 0 or 1");
+    h->opt_cluster_rows = value;
   } else if (!strcmp(key, "fused_steps")) {
     if (value < 2 || value > lbm::kHalo) return fail(LBM_B200_ERR_ARG, "fused_steps must be 2, 3 or 4");
     h->opt_fused_steps = value;
@@ -1810,12 +1883,13 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   lbm_b200_sync(h);
   destroy_graphs(h);
   const bool was_fused = h->fused2;
+  const int was_fusedk = h->fusedk;
   plan(h);
   if (!strcmp(key, "kernel") || !strcmp(key, "fused2")) {
     int rc = resync_flags(h);
     if (rc) return rc;
   }
-  if (h->fused2 && !was_fused) {           // whichever option brought the two-steps-per-pass kernel back on a ring
+  if ((h->fused2 && !was_fused) || (h->fusedk && !was_fusedk)) {   // whichever option brought a fused kernel (or its deeper halo) back on a ring
     int rc = pull_halos(h);
     if (rc) return rc;
   }
@@ -1828,6 +1902,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->cluster ? 6 : (h->fused2 ? (h->fusedk ? 7 : 5) : (h->resident ? 3 : (use_vec4(h) ? 2 : 1))));
   else if (!strcmp(key, "fused_steps")) *value = h->fused2 ? (h->fusedk ? h->fusedk : 2) : 1;
   else if (!strcmp(key, "cluster")) *value = h->cluster ? 1 : 0;
+  else if (!strcmp(key, "cluster_rows")) *value = (h->cluster && h->cluster_rows) ? 1 : 0;
   else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;

@@ -36,6 +36,9 @@ def main(out_path):
         sim.set_option("band_rows", 8)
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") == 5
+        if os.environ.get("LBM_TEST_FUSED_STEPS"):
+            sim.set_option("fused_steps", int(os.environ["LBM_TEST_FUSED_STEPS"]))
+            assert sim.get_option("kernel") == 7
     dist.barrier()
     av = torch.from_numpy(sim.run(iters).copy())
     dist.barrier()

@@ -59,6 +59,29 @@ def test_fused2_across_devices(pkg, oracle, n):
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
+@pytest.mark.parametrize("steps", [3, 4])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_k_steps_per_pass_across_devices(pkg, oracle, n, steps):
+    """Kernel 7 on a ring of real devices: four halo rows per side over NVLink, one strip-level flag handshake per
+    pass of three / four timesteps, shorter last passes."""
+    need_gpus(pkg, n)
+    rng = np.random.default_rng(70 + n + steps)
+    nx, ny, iters = 600, 11 * n + 3, 202
+    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    cells0 = random_cells(rng, ny, nx)
+    ref = cells0.copy()
+    ref_av = oracle.run(ref, obstacles, iters + 31, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n) as sim:
+        sim.set_option("band_rows", 4)
+        sim.set_option("fused2", 1)
+        sim.set_option("fused_steps", steps)
+        assert sim.get_option("kernel") == 7
+        sim.set_cells(cells0)
+        av = np.concatenate([sim.run(iters), sim.run(31)])
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))
+        assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
 @pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("n", [2, 8])
 def test_graph_replay_across_devices(pkg, oracle, n, inplace):
@@ -80,7 +103,7 @@ def test_graph_replay_across_devices(pkg, oracle, n, inplace):
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
-@pytest.mark.parametrize("inplace", [False, True, "fused2"])
+@pytest.mark.parametrize("inplace", [False, True, "fused2", "fused4"])
 @pytest.mark.parametrize("n", [2, 4, 8])
 def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
     """torchrun-style launch: n processes, CUDA IPC handles exchanged with torch.distributed."""
@@ -94,7 +117,8 @@ def test_one_rank_per_gpu_over_ipc(pkg, oracle, n, inplace, tmp_path):
            os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
                          env={**os.environ, "LBM_TEST_INPLACE": "1" if inplace is True else "0",
-                              "LBM_TEST_FUSED2": "1" if inplace == "fused2" else "0"})
+                              "LBM_TEST_FUSED2": "1" if inplace in ("fused2", "fused4") else "0",
+                              "LBM_TEST_FUSED_STEPS": "4" if inplace == "fused4" else ""})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     data = np.load(out)
     obstacles, cells = data["obstacles"], data["cells"]

@@ -148,20 +148,27 @@ def test_fused_deep_variant_is_bit_identical(pkg, oracle, iters):
             assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
 
 
-@pytest.mark.parametrize("shape", [(128, 128), (128, 256), (64, 48), (200, 32)])
-def test_cluster_resident_kernel_is_bit_identical(pkg, oracle, shape):
-    """Kernel 6: the grid in the shared memory of one 16-CTA cluster, halo rows over DSMEM.  Random obstacles, an
-    arbitrary initial state, runs that are odd, even, longer than one 256-step launch, and back to back."""
+@pytest.mark.parametrize("shape,rows_form", [((128, 128), 1), ((128, 256), 1), ((128, 16), 1), ((128, 48), 1),
+                                             ((128, 128), 0), ((128, 256), 0), ((64, 48), 0), ((200, 32), 0)])
+def test_cluster_resident_kernel_is_bit_identical(pkg, oracle, shape, rows_form):
+    """Kernel 6: the grid in the shared memory of one 16-CTA cluster, halo rows over DSMEM -- the general form (any
+    nx, remote loads) and the one-warp-per-row form for nx = 128 (packed pairs, pushed halo rows, 1 .. 16 rows per
+    CTA).  Random obstacles on every edge, an arbitrary initial state, runs that are odd, even, longer than one
+    256-step launch, and back to back."""
     nx, ny = shape
     rng = np.random.default_rng(nx + ny)
-    obstacles = random_obstacles(rng, ny, nx, 0.06)
+    obstacles = random_obstacles(rng, ny, nx, 0.06, walls=(rows_form == 0))
+    obstacles[ny - 2, :] = rng.random(nx) < 0.2                # blocked cells in the driven row
     cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, : nx // 3, 3] = 1e-5                        # ... and cells the body force skips
     ref = cells0.copy()
     runs = (7, 300, 1, 256)
     ref_av = oracle.run(ref, obstacles, sum(runs), DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+        sim.set_option("cluster_rows", rows_form)
         sim.set_option("cluster", 1)
         assert sim.get_option("kernel") == 6 and sim.get_option("cluster") == 1
+        assert sim.get_option("cluster_rows") == rows_form
         sim.set_cells(cells0)
         av = np.concatenate([sim.run(n) for n in runs])
         assert np.array_equal(bits(sim.get_cells()), bits(ref))
@@ -208,3 +215,64 @@ def test_k_steps_per_pass_kernel_is_bit_identical(pkg, oracle, steps, stage_rows
         av = np.concatenate([sim.run(n) for n in runs])
         assert np.array_equal(bits(sim.get_cells()), bits(ref))
         assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+
+
+@pytest.mark.parametrize("iters", [3, 7, 12])
+@pytest.mark.parametrize("steps", [3, 4])
+@pytest.mark.parametrize("n_slabs,nx,ny,band", [(2, 256, 16, 64), (3, 360, 29, 4), (4, 244, 47, 5), (8, 600, 56, 64), (2, 1024, 12, 2)])
+def test_k_steps_ring_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny, band, steps, iters):
+    """Kernel 7 on a ring: four halo rows per side, the steps before the last recomputed for the neighbours' rows,
+    one push of four rows per direction and one flag handshake per pass; shorter last passes through the same strips.
+    Ragged strips, bands of 4..64 rows, slabs of 6..15 rows, the driven row recomputed by the first slab (its row -2),
+    blocked and non-forced cells in it.  Then a second run, kernel 5 and the one-step kernel on the same ring, and
+    back (the deeper halo is fetched again)."""
+    rng = np.random.default_rng(n_slabs * 1000 + nx + iters + steps)
+    obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))
+    obstacles[:, 0] = rng.random(ny) < 0.5
+    obstacles[:, -1] = rng.random(ny) < 0.5
+    obstacles[ny - 2, :] = rng.random(nx) < 0.2
+    cells0 = random_cells(rng, ny, nx)
+    cells0[ny - 2, : nx // 3, 3] = 1e-5
+    inv = pkg.free_cells_inv(obstacles)
+    ref = cells0.copy()
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
+        sim.set_option("band_rows", band)
+        sim.set_option("fused2", 1)
+        sim.set_option("fused_steps", steps)
+        assert sim.get_option("kernel") == 7 and sim.get_option("fused_steps") == steps
+        sim.set_cells(cells0)
+        for n, opts in ((iters, {}), (5, {}), (4, {"fused_steps": 2}), (3, {"fused2": 0}), (6, {"fused2": 1, "fused_steps": steps})):
+            for key, value in opts.items():
+                sim.set_option(key, value)
+            ref_av = oracle.run(ref, obstacles, n, DENSITY, ACCEL, OMEGA, inv)
+            av = sim.run(n)
+            assert np.array_equal(bits(sim.get_cells()), bits(ref)), (n, opts)
+            assert np.max(np.abs(av - ref_av) / ref_av) < 1e-4
+        assert sim.get_option("kernel") == 7
+
+
+def test_k_steps_kernel_is_refused_on_thin_ring_slabs(pkg):
+    ob = np.zeros((15, 256), np.int32)
+    with pkg.Simulation(256, 15, DENSITY, ACCEL, OMEGA, ob, n_slabs=3, device=0) as sim:   # 5 rows per slab: kernel 5 fits, 7 does not
+        sim.set_option("fused2", 1)
+        sim.set_option("fused_steps", 4)
+        assert sim.get_option("kernel") == 5 and sim.get_option("fused_steps") == 2
+
+
+def test_back_to_back_runs_on_a_k_steps_ring(pkg, oracle):
+    """enqueue x 4 without a sync in between on a kernel-7 ring (the pre-pass on the halo copy of the driven row is
+    ordered by the strip flags against the previous run's last pushes)."""
+    rng = np.random.default_rng(6)
+    nx, ny = 480, 45
+    obstacles = random_obstacles(rng, ny, nx, 0.05)
+    ref = oracle.init_cells(nx, ny, DENSITY)
+    oracle.run(ref, obstacles, 7 + 6 + 5 + 2, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
+    with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=4, device=0) as sim:
+        sim.set_option("band_rows", 4)
+        sim.set_option("fused2", 1)
+        sim.set_option("fused_steps", 4)
+        assert sim.get_option("kernel") == 7
+        for it in (7, 6, 5, 2):
+            sim.enqueue(it)
+        sim.sync()
+        assert np.array_equal(bits(sim.get_cells()), bits(ref))

@@ -1,13 +1,13 @@
 #!/bin/bash
 # One single-GPU measurement session on a B200 box (run under gpurun):
-#   tools/gpu_session.sh <out-dir> [stages...]     stages: smoke tests bench benchq ref onestep inplace launches ncu ncu_onestep decks
+#   [NCU_FLAGS="--fused-steps 4"] [NCU_KERNEL=steps_strip] tools/gpu_session.sh <out-dir> [stages...]     stages: smoke tests bench benchq ref onestep inplace launches ncu ncu_onestep decks
 # Each stage writes its own log under <out-dir>; a failing stage does not stop the later ones.
 set -u
 OUT=${1:-gpurun_out/session}; shift || true
 STAGES=${*:-smoke tests bench onestep inplace launches ncu}
 mkdir -p "$OUT"
 cd "$(dirname "$0")/.."
-NCU_CMD="python bench.py --steps 3 --warmup 3 --timesteps 10 --no-cpu-baseline --no-parity --no-e2e"
+NCU_CMD="python bench.py --steps 3 --warmup 3 --timesteps 12 --no-cpu-baseline --no-parity --no-e2e ${NCU_FLAGS:-}"
 for st in $STAGES; do
   case $st in
     smoke)    python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -3 | tee "$OUT/smoke.log" ;;
