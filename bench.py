@@ -392,6 +392,7 @@ def bench_ours(args, pkg):
                             p_first, p_ny, inv=p_inv)
             if kernel in (5, 7):
                 psim.set_option("fused2", 1)             # the timed kernel (automatic only from 2^22 cells per GPU)
+                psim.set_option("fused_steps", fused_steps)   # ... with the timed number of steps per pass
                 if distributed:
                     dist.barrier()                       # every rank has switched before any rank runs
             p_kernel = psim.get_option("kernel")
@@ -598,7 +599,7 @@ def main():
     ap.add_argument("--min-ctas", dest="min_ctas", type=int, default=None)
     ap.add_argument("--fused2", type=int, default=None, choices=[-1, 0, 1],
                     help="two timesteps per pass over HBM: 1 on, 0 off, default automatic (on from 2^22 cells per GPU)")
-    ap.add_argument("--fused-steps", dest="fused_steps", type=int, default=None, choices=[2, 3, 4],
+    ap.add_argument("--fused-steps", dest="fused_steps", type=int, default=None, choices=[0, 2, 3, 4],
                     help="timesteps per pass over HBM of the fused kernel (2 = kernel 5, 3 or 4 = kernel 7)")
     ap.add_argument("--band-rows", dest="band_rows", type=int, default=None)
     ap.add_argument("--prefetch-rows", dest="prefetch_rows", type=int, default=None, help="kernel 5: L2 prefetch distance in rows")

@@ -126,8 +126,11 @@ struct lbm_b200 {
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
   long opt_cluster = -1;                // kernel 6: -1 automatic, 0 never, 1 wherever it fits
-  long opt_fused_steps = 2;             // timesteps per pass over HBM of the fused kernel: 2 = kernel 5, 3 or 4 = kernel 7
-  long opt_fused_deep = 1;              // kernel 5: two staging rows, 3 CTAs x 4 warps per SM (+3 %, profiles/r02_fused2.md)
+  long opt_fused_steps = 0;             // timesteps per pass over HBM of the fused kernel: 2 = kernel 5, 3 or 4 = kernel 7,
+                                        // 0 = automatic (fused_steps_wanted)
+  long opt_fused_deep = -1;             // staging rows of the fused kernels: 1 = two (the copy runs two rows ahead), 0 = one,
+                                        // -1 = automatic: two for kernel 5 (3 CTAs x 4 warps per SM, +3 %), one for kernel 7
+                                        // (more resident warps instead, +5..25 %; profiles/r02_fused2.md)
   long opt_prefetch_rows = 0;           // kernel 5: L2 prefetch distance in rows (0 = off: measured slower, profiles/r02_fused2.md)
   long opt_spin_timeout_ms = 30000;     // how long a kernel waits for a ring neighbour's flag before it gives up
   long opt_debug_skip_slab = -1;        // test hook: this slab's step kernels are not launched (its neighbours time out)
@@ -284,6 +287,13 @@ bool want_fused2(const lbm_b200* h)
 constexpr int fused_warps(bool deep) { return deep ? 4 : 8; }
 constexpr size_t fused_smem(bool deep) { return (size_t)fused_warps(deep) * lbm::fused_warp_float4(deep) * sizeof(float4); }
 
+// staging rows of the fused kernel in use (see opt_fused_deep)
+int stage_rows(const lbm_b200* h)
+{
+  if (h->opt_fused_deep >= 0) return h->opt_fused_deep != 0 ? 2 : 1;
+  return h->fusedk ? 1 : 2;
+}
+
 // Launch shape of kernel 7 for k steps per pass and d staging rows: warps per CTA x CTAs per SM = the warps whose
 // rings and staging rows fit into an SM's shared memory (lbm::stepsk_max_warps).
 void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm)
@@ -318,9 +328,20 @@ int y_of_padded(int rows, int r)
 }
 
 // Kernel 7 (K = 3 or 4 timesteps per pass) where kernel 5 applies, K was asked for and the rows allow it.
+// Timesteps per pass of the fused kernel.  Automatic (profiles/r02_fused2.md, one B200): kernel 7 needs 19..28 KB of
+// shared memory per warp, so only 8..11 warps are resident per SM and a pass has fewer, longer work items; it wins
+// from 2^26 cells per GPU with K = 4 (8192^2: 167.7 vs 156.6 GLUPS, 16384^2: 176.6 vs 157.9), by 2 % with K = 3 at
+// 2^25 (16384 x 2048), and loses below (4096^2: 105..119 vs 143).
+int fused_steps_wanted(const lbm_b200* h)
+{
+  if (h->opt_fused_steps != 0) return (int)h->opt_fused_steps;
+  const long cells = (long)h->nx * h->ny / h->n_ranks;
+  return cells >= (1L << 26) ? 4 : (cells >= (1L << 25) ? 3 : 2);
+}
+
 bool want_fusedk(const lbm_b200* h)
 {
-  if (h->opt_fused_steps < 3) return false;
+  if (fused_steps_wanted(h) < 3) return false;
   if (h->n_ranks == 1) return h->ny >= 2 * lbm::kHalo;
   // a ring: every slab holds its neighbours' kHalo rows, and the driven row ny-2 must not be a row a slab other than
   // the one north of its owner recomputes (a whole-domain handle sees all slabs, a one-slab-per-process handle its
@@ -350,7 +371,9 @@ void plan_bands_k(int rows, int nx, int band_rows, int sms, int k, int warps_per
       // ragged end of ~0.6 item; a launch whose items all fit at once runs every warp in the same phase (1.37 x
       // slower per row than the steady state) and no faster than a warp alone can go (0.63 of a full SM's pace).
       const double fill = (double)nb * strips / (double)slots;
-      const double cost = (per_b + 2.0 * (k - 1) + 0.5) * (fill > 1.0 ? fill + 0.62 : 1.37 * std::max(0.63, fill));
+      // (k >= 3: + the walk's start-up and drain -- 192-row bands measured 1.7 % faster than 128 at 16384^2, k = 4)
+      const double over = 2.0 * (k - 1) + (k >= 3 ? 4.0 : 0.5);
+      const double cost = (per_b + over) * (fill > 1.0 ? fill + 0.62 : 1.37 * std::max(0.63, fill));
       if (want <= 0 || cost < best) { best = cost; want = b; }
     }
   }
@@ -370,7 +393,7 @@ void plan(lbm_b200* h)
   h->fused2 = want_fused2(h);
   h->cluster = !(h->fused2 && h->opt_fused2 == 1) && want_cluster(h);
   if (h->cluster) h->resident = h->fused2 = false;
-  h->fusedk = (h->fused2 && want_fusedk(h)) ? (int)h->opt_fused_steps : 0;
+  h->fusedk = (h->fused2 && want_fusedk(h)) ? fused_steps_wanted(h) : 0;
   if (h->fused2) {
     h->resident = false;
     h->fused_strips = (h->nx + lbm::kStripOut - 1) / lbm::kStripOut;
@@ -379,13 +402,13 @@ void plan(lbm_b200* h)
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
       int bands = 1, per = s.rows;
       int k7_wpc = 0, k7_ctas = 0;
-      if (h->fusedk) stepsk_shape(h->fusedk, h->opt_fused_deep != 0 ? 2 : 1, &k7_wpc, &k7_ctas);
-      const int resident_warps = h->fusedk ? k7_wpc * k7_ctas : (h->opt_fused_deep != 0 ? 12 : 16);
+      if (h->fusedk) stepsk_shape(h->fusedk, stage_rows(h), &k7_wpc, &k7_ctas);
+      const int resident_warps = h->fusedk ? k7_wpc * k7_ctas : (stage_rows(h) == 2 ? 12 : 16);
       plan_bands_k(s.rows, h->nx, (int)h->opt_band_rows, sms, h->fusedk ? h->fusedk : 2, resident_warps, h->n_ranks > 1, &bands, &per);
       s.fused_bands = bands;
       s.fused_band_rows = per;
       const long items = (long)h->fused_strips * bands;
-      const int wpc = h->fusedk ? k7_wpc : fused_warps(h->opt_fused_deep != 0);
+      const int wpc = h->fusedk ? k7_wpc : fused_warps(stage_rows(h) == 2);
       s.fused_grid = (int)std::min<long>((items + wpc - 1) / wpc, 1L << 30);
       if (h->opt_ctas_per_sm > 0) {
         int sms = 148;
@@ -807,7 +830,7 @@ int enqueue_fused2(lbm_b200* h, int slot, bool fold_last, bool single)
     g.fold_last = fold_last ? 1 : 0;
     g.partial_stride = s.per_step;
     g.prefetch_rows = (int)h->opt_prefetch_rows;
-    const bool deep = h->opt_fused_deep != 0;
+    const bool deep = stage_rows(h) == 2;
     const size_t kFusedSmem = fused_smem(deep);
     const dim3 grid(s.fused_grid), block(fused_warps(deep) * 32);
     if (h->n_ranks == 1) {
@@ -897,7 +920,7 @@ int enqueue_fusedk(lbm_b200* h, int slot, int k, bool fold_last)
       if (s.first_row == 0 && s.accel_row < 0) g.accel_y = -2;
     }
     int rc;
-    switch ((peer ? 100 : 0) + k * 10 + (h->opt_fused_deep != 0 ? 2 : 1)) {
+    switch ((peer ? 100 : 0) + k * 10 + stage_rows(h)) {
       case 11: rc = launch_stepsk<1, 1, false>(h, s, a, g); break;
       case 12: rc = launch_stepsk<1, 2, false>(h, s, a, g); break;
       case 21: rc = launch_stepsk<2, 1, false>(h, s, a, g); break;
@@ -1072,8 +1095,8 @@ void init_common(lbm_b200* h, int nx, int ny, float density, float accel, float 
   if (const char* e = getenv("LBM_B200_BAND_ROWS")) h->opt_band_rows = std::max(0L, atol(e));
   if (const char* e = getenv("LBM_B200_CLUSTER")) h->opt_cluster = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_CLUSTER_ROWS")) h->opt_cluster_rows = atol(e) != 0;
-  if (const char* e = getenv("LBM_B200_FUSED_STEPS")) h->opt_fused_steps = std::max(2L, std::min((long)lbm::kHalo, atol(e)));
-  if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = atol(e) != 0;
+  if (const char* e = getenv("LBM_B200_FUSED_STEPS")) h->opt_fused_steps = std::max(0L, std::min((long)lbm::kHalo, atol(e)));
+  if (const char* e = getenv("LBM_B200_FUSED_DEEP")) h->opt_fused_deep = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("LBM_B200_PREFETCH_ROWS")) h->opt_prefetch_rows = std::max(0L, std::min(16L, atol(e)));
 }
 
@@ -1853,7 +1876,7 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster_rows must be 0 or 1");
     h->opt_cluster_rows = value;
   } else if (!strcmp(key, "fused_steps")) {
-    if (value < 2 || value > lbm::kHalo) return fail(LBM_B200_ERR_ARG, "fused_steps must be 2, 3 or 4");
+    if (value != 0 && (value < 2 || value > lbm::kHalo)) return fail(LBM_B200_ERR_ARG, "fused_steps must be 0 (automatic), 2, 3 or 4");
     h->opt_fused_steps = value;
   } else if (!strcmp(key, "band_rows")) {
     if (value < 0 || value > (1 << 20)) return fail(LBM_B200_ERR_ARG, "band_rows must be 0 (automatic) .. 2^20");
@@ -1862,7 +1885,7 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
     if (value < 1) return fail(LBM_B200_ERR_ARG, "staging_bytes must be positive");
     h->opt_staging_bytes = value;
   } else if (!strcmp(key, "fused_deep")) {
-    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "fused_deep must be 0 or 1");
+    if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "fused_deep must be -1, 0 or 1");
     h->opt_fused_deep = value;
   } else if (!strcmp(key, "prefetch_rows")) {
     if (value < 0 || value > 16) return fail(LBM_B200_ERR_ARG, "prefetch_rows must be 0 .. 16");
@@ -1908,7 +1931,7 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   else if (!strcmp(key, "inplace")) *value = h->inplace ? 1 : 0;
   else if (!strcmp(key, "staging_bytes")) *value = h->opt_staging_bytes;
   else if (!strcmp(key, "prefetch_rows")) *value = h->opt_prefetch_rows;
-  else if (!strcmp(key, "fused_deep")) *value = h->opt_fused_deep;
+  else if (!strcmp(key, "fused_deep")) *value = stage_rows(h) - 1;
   else if (!strcmp(key, "spin_timeout_ms")) *value = h->opt_spin_timeout_ms;
   else if (!strcmp(key, "debug_skip_slab")) *value = h->opt_debug_skip_slab;
   else if (!strcmp(key, "graph_steps")) *value = h->opt_graph_steps;

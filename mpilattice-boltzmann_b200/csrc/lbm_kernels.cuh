@@ -738,12 +738,14 @@ __device__ __forceinline__ void stg2(float* p, f2 a, f2 b)
 }
 
 // The rare path of collide_quad: a row segment with obstacles, or the driven row (the body force folded in).  Kept out
-// of line so that the common path's register allocation does not pay for it.  `blocked` is in pair order (bit 0..3 =
-// first / second cell of p, first / second cell of q).
-__device__ __noinline__ void collide_quad_masked_call(f2 (&p)[9], f2 (&q)[9], unsigned blocked, const StepConst& c, bool fold,
-                                                      float2& up, float2& uq)
+// of line -- with nothing but one array and scalars crossing the call: every other interface tried (the pairs
+// themselves, a StepConst reference, results through references) cost the COMMON path 3..7 % through its register
+// allocation (same-box A/B, profiles/r02_fused2.md).
+__device__ __noinline__ float collide4_generic(float (&f)[4][9], unsigned bits, float omega, bool fold, float aw1, float aw2, float nz)
 {
-  collide_pairs_masked(p, q, blocked, c, fold, up, uq);
+  StepConst c;
+  c.omega = omega; c.aw1 = aw1; c.aw2 = aw2; c.negzero = nz;
+  return collide4_masked(f, bits, c, fold);
 }
 
 // A lane's four cells as two packed pairs.  ROT = false: p = cells (0,1), q = cells (2,3); ROT = true: p = cells
@@ -766,9 +768,20 @@ __host__ __device__ __forceinline__ unsigned pair_order(unsigned bits, bool rot)
 template <bool ROT>
 __device__ __forceinline__ float collide_quad_generic(f2 (&p)[9], f2 (&q)[9], unsigned bits, const StepConst& c, bool fold)
 {
-  float2 up, uq;
-  collide_quad_masked_call(p, q, pair_order(bits, ROT), c, fold, up, uq);
-  return ROT ? add(add(add(uq.y, up.x), up.y), uq.x) : add(add(add(up.x, up.y), uq.x), uq.y);
+  float f[4][9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const float2 a = unpack2(p[k]), b = unpack2(q[k]);
+    if (ROT) { f[1][k] = a.x; f[2][k] = a.y; f[3][k] = b.x; f[0][k] = b.y; }
+    else { f[0][k] = a.x; f[1][k] = a.y; f[2][k] = b.x; f[3][k] = b.y; }
+  }
+  const float u4 = collide4_generic(f, bits, c.omega, fold, c.aw1, c.aw2, c.negzero);
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    if (ROT) { p[k] = pack2(f[1][k], f[2][k]); q[k] = pack2(f[3][k], f[0][k]); }
+    else { p[k] = pack2(f[0][k], f[1][k]); q[k] = pack2(f[2][k], f[3][k]); }
+  }
+  return u4;
 }
 
 // PEER   = a slab of a multi-GPU ring.  Padded rows: 0 / rows+1 are the halo rows next to the slab, rows+2 / rows+3

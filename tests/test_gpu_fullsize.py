@@ -54,9 +54,11 @@ def test_full_size_inplace(pkg, oracle):
             assert np.max(np.abs(av.astype(np.float64) - av_ref) / av_ref) < 2e-6
 
 
-def test_full_size_fused2(pkg, oracle):
-    """Two timesteps per pass at 16384 x 16384 (137 strips of 120 columns -- the last one 64 wide --, 256 bands of 64
-    rows): 7 steps = three fused passes and a single-step tail, against the tiled 128-wide oracle."""
+@pytest.mark.parametrize("steps", [2, 0])
+def test_full_size_fused(pkg, oracle, steps):
+    """Two timesteps per pass (kernel 5) and the automatic choice at this size (kernel 7, four per pass) at 16384 x
+    16384 (137 strips of 120 columns -- the last one 64 wide): 7 steps = three passes of two and a single-step tail, or
+    one pass of four and one of three, against the tiled 128-wide oracle."""
     period, iters = 128, 7
     rng = np.random.default_rng(44)
     narrow = narrow_pattern(period, rng)
@@ -66,7 +68,8 @@ def test_full_size_fused2(pkg, oracle):
     obstacles = np.tile(narrow, (1, NX // period))
     with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         sim.set_option("fused2", 1)
-        assert sim.get_option("kernel") == 5
+        sim.set_option("fused_steps", steps)
+        assert (sim.get_option("kernel"), sim.get_option("fused_steps")) == ((5, 2) if steps == 2 else (7, 4))
         av = sim.run(iters)
         assert sim.get_option("launches") < 12
         for got, want in zip(sim.final_state(), ref_fields):
