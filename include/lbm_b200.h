@@ -182,26 +182,36 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
 /* Tuning knobs, all optional.  Unknown keys fail with LBM_B200_ERR_ARG.
  *   "kernel"        0 = auto, 1 = one cell per thread, 2 = four cells per thread (128-bit); reads back 3
  *                   when the resident variant of kernel 2 is in use, 4 on an in-place handle, 5 when two
- *                   timesteps are fused per pass ("fused2") and 6 when the grid lives in a cluster's shared memory
+ *                   timesteps are fused per pass ("fused2"), 7 when three or four are ("fused_steps") and 6 when the
+ *                   grid lives in a cluster's shared memory
  *   "fused2"        two timesteps per pass over HBM (kernel 5: the first step of a 120-column strip goes into a
  *                   shared-memory ring, the second comes out of it; half the DRAM traffic per step, bit-identical
  *                   results; ring slabs keep two halo rows per side and exchange once per pass).  1 = on where it
  *                   applies (ping-pong handle, nx % 4 == 0, nx >= 240, >= 4 rows per slab), 0 = off, -1 = automatic
- *                   (on from 2^22 cells per GPU).  Reads back whether it is in use; "kernel" then reads 5.
+ *                   (on from 2^22 cells per GPU).  Reads back whether it is in use; "kernel" then reads 5 or 7.
  *                   On a multi-process ring set it on every rank while the ring is idle.
+ *   "fused_steps"   timesteps per pass over HBM where "fused2" is in use: 2 = kernel 5; 3 or 4 = kernel 7 (a chain
+ *                   of shared-memory rings, one per intermediate step; a third / a quarter of the DRAM traffic per
+ *                   step; ring slabs keep four halo rows per side and need >= 6 rows each); 0 = automatic (4 from
+ *                   2^26 cells per GPU, 3 from 2^25, else 2).  Reads back the number in use (1 without "fused2").
+ *                   Runs whose length is not a multiple end with a shorter pass through the same kernel.
  *   "cluster"       kernel 6: the whole grid resident in the shared memory of ONE 16-CTA thread-block cluster for up
  *                   to 256 timesteps per launch, halo rows read from the neighbour CTA over distributed shared
  *                   memory, one hardware cluster barrier per step (for launch-latency-bound decks: 128 x 128 and
  *                   128 x 256 fit; single-GPU ping-pong handles with ny % 16 == 0).  1 = wherever it fits, 0 = never,
  *                   -1 = automatic (where it fits and no other kernel / launch mode was asked for).  Reads back
  *                   whether it is in use; "kernel" then reads 6.
- *   "fused_deep"    kernel 5: 1 (default) = two staging rows, the copy runs two rows ahead of the arithmetic, 3 CTAs
- *                   x 4 warps per SM; 0 = one staging row, 2 CTAs x 8 warps per SM
+ *   "cluster_rows"  kernel 6 on 128-cell-wide grids of up to 256 rows: 1 (default) = one warp per row for the whole
+ *                   launch, packed-pair arithmetic, halo rows pushed into the neighbour CTA (kernel 6b: 1.6 us per
+ *                   step on the 128 x 128 deck instead of 2.3), 0 = the general form.  Reads back which one runs.
+ *   "fused_deep"    staging rows of kernels 5 and 7: 1 = two (the copy runs two rows ahead of the arithmetic; kernel 5:
+ *                   3 CTAs x 4 warps per SM), 0 = one (kernel 5: 2 CTAs x 8 warps; kernel 7: more resident warps),
+ *                   -1 (default) = automatic: two for kernel 5, one for kernel 7.  Reads back 0 or 1.
  *   "prefetch_rows" kernel 5: bulk L2 prefetch this many rows ahead of the copy (default 0 = off: measured slower)
  *   "spin_timeout_ms"  how long a kernel of a ring slab waits for a neighbour's halo flag before it gives up and
  *                   lbm_b200_sync reports LBM_B200_ERR_STATE (default 30000)
  *   "debug_skip_slab"  test hook: the step kernels of this slab of a whole-domain handle are not launched
- *   "band_rows"     rows per work item of kernel 5 (0 = automatic)
+ *   "band_rows"     rows per work item of kernels 5 and 7 (0 = automatic)
  *   "inplace"       read-only: 1 on a handle made by lbm_b200_create_inplace
  *   "staging_bytes" in-place handles: size of the device staging buffer that get_cells / set_cells /
  *                   get_final_state move the state through, in chunks of whole rows (default 256 MB)
