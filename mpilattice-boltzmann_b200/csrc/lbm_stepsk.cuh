@@ -55,6 +55,249 @@ __host__ __device__ constexpr int stepsk_max_warps(int k, int d)
   return (int)((232448 - 3 * 1280) / stepsk_warp_bytes(k, d)) > 12 ? 12 : (int)((232448 - 3 * 1280) / stepsk_warp_bytes(k, d));
 }
 
+// One work item: the walk of one warp down one strip of one band.  EDGE (ring slabs only): the band touches the slab's
+// first or last row -- halo rows, flag handshake and pushes; every other band of a ring slab runs exactly the
+// single-GPU code.  acc[s] += the item's share of step s+1's Sigma |m|/rho.
+template <int K, int D, int HINT, bool EDGE>
+__device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs& g, const int band, const int strip,
+                                            float4* const ring0, const float4* const stage0, const int lane, double (&acc)[K])
+{
+  const unsigned stage0_s = (unsigned)__cvta_generic_to_shared(stage0);
+  const float* __restrict__ src = a.src;
+  float* __restrict__ dst = a.dst;
+  const size_t P = a.plane;
+  const int rows = a.row_last;                               // owned padded rows are 1..rows
+  const int nx = a.nx;
+
+  // padded row of the 0-based row y in [-kHalo, rows+kHalo): halo rows at a ring slab's edges, periodic otherwise
+  auto prow = [&](const int y) -> int {
+    if ((unsigned)y < (unsigned)rows) return y + 1;     // an owned row: the common case
+    if (EDGE) {
+      if (y < 0) return y == -1 ? 0 : rows - 2 * (y + 1);            // d = -y: rows + 2(d-1)
+      return y == rows ? rows + 1 : rows + 2 * (y - rows) + 1;        // d = y-rows+1: rows + 2(d-1) + 1
+    }
+    return (y < 0) ? y + rows + 1 : y - rows + 1;
+  };
+  // row of obstacle words: the slab's own rows, then (ring) the neighbours' rows in the order of the halo rows
+  auto mrow = [&](const int y) -> int {
+    if ((unsigned)y < (unsigned)rows) return y;
+    if (EDGE) return (y < 0) ? rows - 2 * (y + 1) : rows + 2 * (y - rows) + 1;
+    return (y < 0) ? y + rows : y - rows;
+  };
+  // the row a 0-based y stands for when it is compared with accel_y (periodic on one GPU)
+  auto ident = [&](const int y) -> int {
+    if (EDGE || (unsigned)y < (unsigned)rows) return y;
+    return (y < 0) ? y + rows : y - rows;
+  };
+  const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
+  const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
+  // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
+  int gx = strip * kStripOut - 4 + 4 * lane;
+  if (gx < 0) gx += nx;
+  while (gx >= nx) gx -= nx;
+  const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
+  const uint32_t* const mask_x = a.mask + (gx >> 5);
+  const int mask_shift = gx & 31;
+
+  if (EDGE) {
+    // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
+    if (yb == 0) strip_wait(a, a.wait_from_south, kWaitFromSouth, strip, g.strips, lane);
+    if (ye == rows) strip_wait(a, a.wait_from_north, kWaitFromNorth, strip, g.strips, lane);
+  }
+
+  // ---- asynchronous copy of what the first step of row q_y pulls, into a staging row; returns the row's
+  //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
+  int q_y = yb - (K - 1);
+  int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
+  unsigned stage_s = stage0_s;                            // where the next copy goes
+  const float4* stage = stage0;                           // what the next first step reads
+  auto issue = [&]() -> unsigned {
+    const float* pc = src + ((unsigned)q_c * (unsigned)nx + (unsigned)gx);
+    const float* ps = src + ((unsigned)q_s * (unsigned)nx + (unsigned)gx);
+    const float* pn = src + ((unsigned)q_n * (unsigned)nx + (unsigned)gx);
+    cp_async16(stage_s + 0 * 512, pc + 0 * P);
+    cp_async16(stage_s + 1 * 512, pc + 1 * P);
+    cp_async16(stage_s + 2 * 512, ps + 2 * P);
+    cp_async16(stage_s + 3 * 512, pc + 3 * P);
+    cp_async16(stage_s + 4 * 512, pn + 4 * P);
+    cp_async16(stage_s + 5 * 512, ps + 5 * P);
+    cp_async16(stage_s + 6 * 512, ps + 6 * P);
+    cp_async16(stage_s + 7 * 512, pn + 7 * P);
+    cp_async16(stage_s + 8 * 512, pn + 8 * P);
+    cp_async_commit();
+    if (D == 2) stage_s ^= (stage0_s ^ (stage0_s + kStageSlot * 16));   // the other staging row next time
+    const unsigned word = __ldg(mask_x + (unsigned)mrow(q_y) * (unsigned)a.mask_row_words);   // used rows later
+    q_y++;
+    q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
+    return word;
+  };
+
+  // ---- a finished (owned) row y in column order: to the destination buffer and, on a ring, into the
+  //      neighbours' halo rows (all nine planes of the kHalo rows next to either edge) ----
+  auto emit = [&](const int y, const f2 (&p)[9], const f2 (&q)[9]) {
+    float* const d = dst + ((unsigned)(y + 1) * (unsigned)nx + (unsigned)gx);
+#pragma unroll
+    for (int k = 0; k < 9; k++) stg2<HINT>(d + k * P, p[k], q[k]);
+    if (EDGE) {
+      if (y < kHalo) {                                     // row y of this slab = row south_rows + y of the southern one
+        const int r = (y == 0) ? g.south_rows + 1 : g.south_rows + 2 * y + 1;
+        float* const t = a.south_dst + ((size_t)r * nx + gx);
+#pragma unroll
+        for (int k = 0; k < 9; k++) stg2<0>(t + k * a.south_plane, p[k], q[k]);
+      }
+      if (y >= rows - kHalo) {                             // = row y - rows of the northern one
+        const int dd = rows - y;                           // 1..kHalo
+        const int r = (dd == 1) ? 0 : g.north_rows + 2 * (dd - 1);
+        float* const t = a.north_dst + ((size_t)r * nx + gx);
+#pragma unroll
+        for (int k = 0; k < 9; k++) stg2<0>(t + k * a.north_plane, p[k], q[k]);
+      }
+    }
+  };
+  // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
+  auto publish = [&](const int y) {
+    if (EDGE) {
+      if (y == kHalo - 1) strip_signal(a, a.signal_south, strip, lane);
+      if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
+    }
+  };
+
+  f2 kp[3], kq[3];                                         // planes 4,7,8 of the row the previous step just finished
+  // ring rows (float4 offsets inside a ring): planes 0,1,3 of the row being written / the row read now, planes
+  // 2,5,6 of the row read now (y-1), the row in between, the row being written
+  int a_w = 0, a_r = kRingA;
+  int o_s = 2 * kRingA, o_c = 2 * kRingA + kRingB, o_n = 2 * kRingA + 2 * kRingB;
+
+  // ---- step S (1..K) of row y.  Odd steps: operands in column order (lo = columns 0,1 of the lane's group, hi
+  //      = columns 2,3), cells run as the pairs (1,2) and (3,0), results rotated.  Even steps: operands rotated
+  //      (lo = columns 1,2, hi = columns 3,0), cells run as the pairs (0,1) and (2,3), results in column order.
+  //      Either way only the three unshifted planes need register moves (lbm_kernels.cuh, collide_quad). ----
+  auto step = [&](auto s_tag, const int y, const unsigned mword, const bool ahead, const bool more_pending) -> unsigned {
+    constexpr int S = decltype(s_tag)::value;
+    constexpr bool ODD = (S & 1) != 0, LAST = (S == K);
+    f2 lo[9], hi[9];
+    if (S == 1) {
+      // (D = 2: the copy for the row after this one is in flight as well and may stay so)
+      if (D == 2 && more_pending) cp_async_wait_but_one(); else cp_async_wait_all();
+#pragma unroll
+      for (int k = 0; k < 9; k++) lds2(stage + k * 32, lo[k], hi[k]);
+      if (D == 2) stage = (stage == stage0) ? stage0 + kStageSlot : stage0;
+    } else {
+      const float4* const rg = ring0 + (S - 2) * kRingK;
+      const float4* const s_c = rg + a_r;
+      const float4* const s_s = rg + o_s;
+      lds2(s_c + 0 * 32, lo[0], hi[0]); lds2(s_c + 1 * 32, lo[1], hi[1]); lds2(s_c + 2 * 32, lo[3], hi[3]);
+      lds2(s_s + 0 * 32, lo[2], hi[2]); lds2(s_s + 1 * 32, lo[5], hi[5]); lds2(s_s + 2 * 32, lo[6], hi[6]);
+      lo[4] = kp[0]; hi[4] = kq[0]; lo[7] = kp[1]; hi[7] = kq[1]; lo[8] = kp[2]; hi[8] = kq[2];
+    }
+    // what crosses the lanes: the east-moving populations' column 3 goes to the next lane (its cell 0 pulls it),
+    // the west-moving ones' column 0 to the previous lane
+    const float up1 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[1]) : lo2(hi[1]), 1);
+    const float up5 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[5]) : lo2(hi[5]), 1);
+    const float up8 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[8]) : lo2(hi[8]), 1);
+    const float dn3 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[3]) : hi2(hi[3]), 1);
+    const float dn6 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[6]) : hi2(hi[6]), 1);
+    const float dn7 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[7]) : hi2(hi[7]), 1);
+    // every lane has read its own staging cells (the shuffles consumed them): the copy D rows ahead may start
+    unsigned word_next = 0u;
+    if (S == 1 && ahead) word_next = issue();
+    const unsigned bits = (mword >> mask_shift) & 0xFu;
+    const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
+    if (LAST && !ODD && !owned) return word_next;
+    const bool fold = (LAST ? g.fold_last != 0 : true) && (ident(y) == g.accel_y);
+    f2 p[9], q[9];
+    if (ODD) {                                             // p = cells (1,2), q = cells (3,0)
+      p[0] = pack2(hi2(lo[0]), lo2(hi[0])); q[0] = pack2(hi2(hi[0]), lo2(lo[0]));
+      p[2] = pack2(hi2(lo[2]), lo2(hi[2])); q[2] = pack2(hi2(hi[2]), lo2(lo[2]));
+      p[4] = pack2(hi2(lo[4]), lo2(hi[4])); q[4] = pack2(hi2(hi[4]), lo2(lo[4]));
+      p[1] = lo[1]; q[1] = pack2(lo2(hi[1]), up1);
+      p[5] = lo[5]; q[5] = pack2(lo2(hi[5]), up5);
+      p[8] = lo[8]; q[8] = pack2(lo2(hi[8]), up8);
+      p[3] = hi[3]; q[3] = pack2(dn3, hi2(lo[3]));
+      p[6] = hi[6]; q[6] = pack2(dn6, hi2(lo[6]));
+      p[7] = hi[7]; q[7] = pack2(dn7, hi2(lo[7]));
+    } else {                                               // p = cells (0,1), q = cells (2,3)
+      p[0] = pack2(hi2(hi[0]), lo2(lo[0])); q[0] = pack2(hi2(lo[0]), lo2(hi[0]));
+      p[2] = pack2(hi2(hi[2]), lo2(lo[2])); q[2] = pack2(hi2(lo[2]), lo2(hi[2]));
+      p[4] = pack2(hi2(hi[4]), lo2(lo[4])); q[4] = pack2(hi2(lo[4]), lo2(hi[4]));
+      p[1] = pack2(up1, hi2(hi[1])); q[1] = lo[1];
+      p[5] = pack2(up5, hi2(hi[5])); q[5] = lo[5];
+      p[8] = pack2(up8, hi2(hi[8])); q[8] = lo[8];
+      p[3] = lo[3]; q[3] = pack2(lo2(hi[3]), dn3);
+      p[6] = lo[6]; q[6] = pack2(lo2(hi[6]), dn6);
+      p[7] = lo[7]; q[7] = pack2(lo2(hi[7]), dn7);
+    }
+    const bool count = owned && y >= yb && y < ye;
+    // (each branch stores its own results: a join would pin 36 registers to common locations)
+    auto finish = [&](const float u4) {
+      acc[S - 1] += (double)(count ? u4 : 0.0f);
+      if (LAST) {
+        if (!ODD) {
+          emit(y, p, q);
+        } else if (owned) {
+          f2 op[9], oq[9];                                 // back to column order: cells (0,1), (2,3)
+#pragma unroll
+          for (int k = 0; k < 9; k++) { op[k] = pack2(hi2(q[k]), lo2(p[k])); oq[k] = pack2(hi2(p[k]), lo2(q[k])); }
+          emit(y, op, oq);
+        }
+        return;
+      }
+      float4* const slot_a = ring0 + (S - 1) * kRingK + a_w;
+      float4* const slot_b = ring0 + (S - 1) * kRingK + o_n;
+      sts2(slot_a + 0 * 32, p[0], q[0]);
+      sts2(slot_a + 1 * 32, p[1], q[1]);
+      sts2(slot_a + 2 * 32, p[3], q[3]);
+      sts2(slot_b + 0 * 32, p[2], q[2]);
+      sts2(slot_b + 1 * 32, p[5], q[5]);
+      sts2(slot_b + 2 * 32, p[6], q[6]);
+      kp[0] = p[4]; kq[0] = q[4]; kp[1] = p[7]; kq[1] = q[7]; kp[2] = p[8]; kq[2] = q[8];
+    };
+    if (!any_blocked && !fold) finish(collide_quad_fast<ODD>(p, q, a.c));
+    else finish(collide_quad_generic<ODD>(p, q, bits, a.c, fold));
+    return word_next;
+  };
+
+  // Walk: iteration r runs step s on row r-(s-1), s = 1..K, as far as that row belongs to the step's range
+  // [yb-(K-s), ye+(K-s)); every range ends exactly with the last iteration.  The copies run D rows ahead;
+  // W[j] = obstacle word of row r+D-1-j, so step s reads W[D-2+s].
+  const int r0 = yb - (K - 1), r_last = ye + K - 2;
+  constexpr int NW = K + D - 1;
+  unsigned W[NW];
+#pragma unroll
+  for (int j = 0; j < NW; j++) W[j] = 0u;
+  W[D - 1] = issue();
+  if (D == 2 && r0 + 1 <= r_last) W[0] = issue();
+#pragma unroll 1
+  for (int r = r0; r <= r_last; r++) {
+    const unsigned w_new = step(std::integral_constant<int, 1>{}, r, W[D - 1], r + D <= r_last, r + 1 <= r_last);
+    if constexpr (K >= 2) { if (r >= yb - K + 3) step(std::integral_constant<int, 2>{}, r - 1, W[D], false, false); }
+    if constexpr (K >= 3) { if (r >= yb - K + 5) step(std::integral_constant<int, 3>{}, r - 2, W[D + 1], false, false); }
+    if constexpr (K >= 4) { if (r >= yb - K + 7) step(std::integral_constant<int, 4>{}, r - 3, W[D + 2], false, false); }
+    // (here, not inside the last step: its two halo lanes leave early, and the flag store is lane 0's)
+    if (r - (K - 1) >= yb) publish(r - (K - 1));
+    const int t = o_s; o_s = o_c; o_c = o_n; o_n = t;
+    const int u = a_w; a_w = a_r; a_r = u;
+#pragma unroll
+    for (int j = NW - 1; j >= 1; j--) W[j] = W[j - 1];
+    W[0] = w_new;
+  }
+}
+
+// The edge items of a ring slab, out of line: with both forms inlined into one kernel body the INTERIOR items of a
+// ring slab ran 3 % slower than the single-GPU kernel (same box, 171.2 vs 177.1 GLUPS per 16384^2 slab,
+// profiles/r02_fused2.md) -- the hot loop's register allocation and layout paid for code it never runs.
+template <int K> struct StepSums { double v[K]; };
+template <int K, int D, int HINT>
+__device__ __noinline__ StepSums<K> stepsk_edge_item(const StepArgs& a, const StepsKArgs& g, const int band, const int strip,
+                                                      float4* const ring0, const float4* const stage0, const int lane)
+{
+  StepSums<K> s;
+#pragma unroll
+  for (int i = 0; i < K; i++) s.v[i] = 0.0;
+  stepsk_item<K, D, HINT, true>(a, g, band, strip, ring0, stage0, lane, s.v);
+  return s;
+}
+
 template <int K, int D, int HINT, bool PEER>
 __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(const StepArgs a, const StepsKArgs g)
 {
@@ -64,12 +307,6 @@ __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   float4* const ring0 = fused_smem + (size_t)warp * stepsk_warp_float4(K, D) + lane;   // this lane's cells of the K-1 rings
   const float4* const stage0 = ring0 + (K - 1) * kRingK;                               // ... and of [D][9][32]
-  const unsigned stage0_s = (unsigned)__cvta_generic_to_shared(stage0);
-  const float* __restrict__ src = a.src;
-  float* __restrict__ dst = a.dst;
-  const size_t P = a.plane;
-  const int rows = a.row_last;                               // owned padded rows are 1..rows
-  const int nx = a.nx;
   double acc[K];
 #pragma unroll
   for (int s = 0; s < K; s++) acc[s] = 0.0;
@@ -81,226 +318,13 @@ __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(co
     // a ring slab does its two edge bands first: their rows are on the way to the neighbours (and published) while
     // the interior bands run, as the reference overlaps its halo exchange with the interior rows (326-366)
     if (PEER && g.bands > 2) band = (band == 0) ? 0 : (band == 1 ? g.bands - 1 : band - 1);
-
-    // One work item.  EDGE (ring slabs only): the band touches the slab's first or last row -- halo rows, flag
-    // handshake and pushes; every other band of a ring slab runs exactly the single-GPU code.
-    auto run_item = [&](auto edge_tag) {
-      constexpr bool EDGE = decltype(edge_tag)::value;
-      // padded row of the 0-based row y in [-kHalo, rows+kHalo): halo rows at a ring slab's edges, periodic otherwise
-      auto prow = [&](const int y) -> int {
-        if ((unsigned)y < (unsigned)rows) return y + 1;     // an owned row: the common case
-        if (EDGE) {
-          if (y < 0) return y == -1 ? 0 : rows - 2 * (y + 1);            // d = -y: rows + 2(d-1)
-          return y == rows ? rows + 1 : rows + 2 * (y - rows) + 1;        // d = y-rows+1: rows + 2(d-1) + 1
-        }
-        return (y < 0) ? y + rows + 1 : y - rows + 1;
-      };
-      // row of obstacle words: the slab's own rows, then (ring) the neighbours' rows in the order of the halo rows
-      auto mrow = [&](const int y) -> int {
-        if ((unsigned)y < (unsigned)rows) return y;
-        if (EDGE) return (y < 0) ? rows - 2 * (y + 1) : rows + 2 * (y - rows) + 1;
-        return (y < 0) ? y + rows : y - rows;
-      };
-      // the row a 0-based y stands for when it is compared with accel_y (periodic on one GPU)
-      auto ident = [&](const int y) -> int {
-        if (EDGE || (unsigned)y < (unsigned)rows) return y;
-        return (y < 0) ? y + rows : y - rows;
-      };
-      const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
-      const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
-      // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
-      int gx = strip * kStripOut - 4 + 4 * lane;
-      if (gx < 0) gx += nx;
-      while (gx >= nx) gx -= nx;
-      const bool owned = lane >= 1 && lane <= 30 && strip * kStripOut + 4 * (lane - 1) < nx;
-      const uint32_t* const mask_x = a.mask + (gx >> 5);
-      const int mask_shift = gx & 31;
-
-      if (EDGE) {
-        // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
-        if (yb == 0) strip_wait(a, a.wait_from_south, kWaitFromSouth, strip, g.strips, lane);
-        if (ye == rows) strip_wait(a, a.wait_from_north, kWaitFromNorth, strip, g.strips, lane);
-      }
-
-      // ---- asynchronous copy of what the first step of row q_y pulls, into a staging row; returns the row's
-      //      obstacle word of this lane's columns (its bits are >> mask_shift) ----
-      int q_y = yb - (K - 1);
-      int q_s = prow(q_y - 1), q_c = prow(q_y), q_n = prow(q_y + 1);
-      unsigned stage_s = stage0_s;                            // where the next copy goes
-      const float4* stage = stage0;                           // what the next first step reads
-      auto issue = [&]() -> unsigned {
-        const float* pc = src + ((unsigned)q_c * (unsigned)nx + (unsigned)gx);
-        const float* ps = src + ((unsigned)q_s * (unsigned)nx + (unsigned)gx);
-        const float* pn = src + ((unsigned)q_n * (unsigned)nx + (unsigned)gx);
-        cp_async16(stage_s + 0 * 512, pc + 0 * P);
-        cp_async16(stage_s + 1 * 512, pc + 1 * P);
-        cp_async16(stage_s + 2 * 512, ps + 2 * P);
-        cp_async16(stage_s + 3 * 512, pc + 3 * P);
-        cp_async16(stage_s + 4 * 512, pn + 4 * P);
-        cp_async16(stage_s + 5 * 512, ps + 5 * P);
-        cp_async16(stage_s + 6 * 512, ps + 6 * P);
-        cp_async16(stage_s + 7 * 512, pn + 7 * P);
-        cp_async16(stage_s + 8 * 512, pn + 8 * P);
-        cp_async_commit();
-        if (D == 2) stage_s ^= (stage0_s ^ (stage0_s + kStageSlot * 16));   // the other staging row next time
-        const unsigned word = __ldg(mask_x + (unsigned)mrow(q_y) * (unsigned)a.mask_row_words);   // used rows later
-        q_y++;
-        q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
-        return word;
-      };
-
-      // ---- a finished (owned) row y in column order: to the destination buffer and, on a ring, into the
-      //      neighbours' halo rows (all nine planes of the kHalo rows next to either edge) ----
-      auto emit = [&](const int y, const f2 (&p)[9], const f2 (&q)[9]) {
-        float* const d = dst + ((unsigned)(y + 1) * (unsigned)nx + (unsigned)gx);
+    if (PEER && (band == 0 || band == g.bands - 1)) {
+      const StepSums<K> s = stepsk_edge_item<K, D, HINT>(a, g, band, strip, ring0, stage0, lane);
 #pragma unroll
-        for (int k = 0; k < 9; k++) stg2<HINT>(d + k * P, p[k], q[k]);
-        if (EDGE) {
-          if (y < kHalo) {                                     // row y of this slab = row south_rows + y of the southern one
-            const int r = (y == 0) ? g.south_rows + 1 : g.south_rows + 2 * y + 1;
-            float* const t = a.south_dst + ((size_t)r * nx + gx);
-#pragma unroll
-            for (int k = 0; k < 9; k++) stg2<0>(t + k * a.south_plane, p[k], q[k]);
-          }
-          if (y >= rows - kHalo) {                             // = row y - rows of the northern one
-            const int dd = rows - y;                           // 1..kHalo
-            const int r = (dd == 1) ? 0 : g.north_rows + 2 * (dd - 1);
-            float* const t = a.north_dst + ((size_t)r * nx + gx);
-#pragma unroll
-            for (int k = 0; k < 9; k++) stg2<0>(t + k * a.north_plane, p[k], q[k]);
-          }
-        }
-      };
-      // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
-      auto publish = [&](const int y) {
-        if (EDGE) {
-          if (y == kHalo - 1) strip_signal(a, a.signal_south, strip, lane);
-          if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
-        }
-      };
-
-      f2 kp[3], kq[3];                                         // planes 4,7,8 of the row the previous step just finished
-      // ring rows (float4 offsets inside a ring): planes 0,1,3 of the row being written / the row read now, planes
-      // 2,5,6 of the row read now (y-1), the row in between, the row being written
-      int a_w = 0, a_r = kRingA;
-      int o_s = 2 * kRingA, o_c = 2 * kRingA + kRingB, o_n = 2 * kRingA + 2 * kRingB;
-
-      // ---- step S (1..K) of row y.  Odd steps: operands in column order (lo = columns 0,1 of the lane's group, hi
-      //      = columns 2,3), cells run as the pairs (1,2) and (3,0), results rotated.  Even steps: operands rotated
-      //      (lo = columns 1,2, hi = columns 3,0), cells run as the pairs (0,1) and (2,3), results in column order.
-      //      Either way only the three unshifted planes need register moves (lbm_kernels.cuh, collide_quad). ----
-      auto step = [&](auto s_tag, const int y, const unsigned mword, const bool ahead, const bool more_pending) -> unsigned {
-        constexpr int S = decltype(s_tag)::value;
-        constexpr bool ODD = (S & 1) != 0, LAST = (S == K);
-        f2 lo[9], hi[9];
-        if (S == 1) {
-          // (D = 2: the copy for the row after this one is in flight as well and may stay so)
-          if (D == 2 && more_pending) cp_async_wait_but_one(); else cp_async_wait_all();
-#pragma unroll
-          for (int k = 0; k < 9; k++) lds2(stage + k * 32, lo[k], hi[k]);
-          if (D == 2) stage = (stage == stage0) ? stage0 + kStageSlot : stage0;
-        } else {
-          const float4* const rg = ring0 + (S - 2) * kRingK;
-          const float4* const s_c = rg + a_r;
-          const float4* const s_s = rg + o_s;
-          lds2(s_c + 0 * 32, lo[0], hi[0]); lds2(s_c + 1 * 32, lo[1], hi[1]); lds2(s_c + 2 * 32, lo[3], hi[3]);
-          lds2(s_s + 0 * 32, lo[2], hi[2]); lds2(s_s + 1 * 32, lo[5], hi[5]); lds2(s_s + 2 * 32, lo[6], hi[6]);
-          lo[4] = kp[0]; hi[4] = kq[0]; lo[7] = kp[1]; hi[7] = kq[1]; lo[8] = kp[2]; hi[8] = kq[2];
-        }
-        // what crosses the lanes: the east-moving populations' column 3 goes to the next lane (its cell 0 pulls it),
-        // the west-moving ones' column 0 to the previous lane
-        const float up1 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[1]) : lo2(hi[1]), 1);
-        const float up5 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[5]) : lo2(hi[5]), 1);
-        const float up8 = __shfl_up_sync(0xffffffffu, ODD ? hi2(hi[8]) : lo2(hi[8]), 1);
-        const float dn3 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[3]) : hi2(hi[3]), 1);
-        const float dn6 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[6]) : hi2(hi[6]), 1);
-        const float dn7 = __shfl_down_sync(0xffffffffu, ODD ? lo2(lo[7]) : hi2(hi[7]), 1);
-        // every lane has read its own staging cells (the shuffles consumed them): the copy D rows ahead may start
-        unsigned word_next = 0u;
-        if (S == 1 && ahead) word_next = issue();
-        const unsigned bits = (mword >> mask_shift) & 0xFu;
-        const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
-        if (LAST && !ODD && !owned) return word_next;
-        const bool fold = (LAST ? g.fold_last != 0 : true) && (ident(y) == g.accel_y);
-        f2 p[9], q[9];
-        if (ODD) {                                             // p = cells (1,2), q = cells (3,0)
-          p[0] = pack2(hi2(lo[0]), lo2(hi[0])); q[0] = pack2(hi2(hi[0]), lo2(lo[0]));
-          p[2] = pack2(hi2(lo[2]), lo2(hi[2])); q[2] = pack2(hi2(hi[2]), lo2(lo[2]));
-          p[4] = pack2(hi2(lo[4]), lo2(hi[4])); q[4] = pack2(hi2(hi[4]), lo2(lo[4]));
-          p[1] = lo[1]; q[1] = pack2(lo2(hi[1]), up1);
-          p[5] = lo[5]; q[5] = pack2(lo2(hi[5]), up5);
-          p[8] = lo[8]; q[8] = pack2(lo2(hi[8]), up8);
-          p[3] = hi[3]; q[3] = pack2(dn3, hi2(lo[3]));
-          p[6] = hi[6]; q[6] = pack2(dn6, hi2(lo[6]));
-          p[7] = hi[7]; q[7] = pack2(dn7, hi2(lo[7]));
-        } else {                                               // p = cells (0,1), q = cells (2,3)
-          p[0] = pack2(hi2(hi[0]), lo2(lo[0])); q[0] = pack2(hi2(lo[0]), lo2(hi[0]));
-          p[2] = pack2(hi2(hi[2]), lo2(lo[2])); q[2] = pack2(hi2(lo[2]), lo2(hi[2]));
-          p[4] = pack2(hi2(hi[4]), lo2(lo[4])); q[4] = pack2(hi2(lo[4]), lo2(hi[4]));
-          p[1] = pack2(up1, hi2(hi[1])); q[1] = lo[1];
-          p[5] = pack2(up5, hi2(hi[5])); q[5] = lo[5];
-          p[8] = pack2(up8, hi2(hi[8])); q[8] = lo[8];
-          p[3] = lo[3]; q[3] = pack2(lo2(hi[3]), dn3);
-          p[6] = lo[6]; q[6] = pack2(lo2(hi[6]), dn6);
-          p[7] = lo[7]; q[7] = pack2(lo2(hi[7]), dn7);
-        }
-        const bool count = owned && y >= yb && y < ye;
-        // (each branch stores its own results: a join would pin 36 registers to common locations)
-        auto finish = [&](const float u4) {
-          acc[S - 1] += (double)(count ? u4 : 0.0f);
-          if (LAST) {
-            if (!ODD) {
-              emit(y, p, q);
-            } else if (owned) {
-              f2 op[9], oq[9];                                 // back to column order: cells (0,1), (2,3)
-#pragma unroll
-              for (int k = 0; k < 9; k++) { op[k] = pack2(hi2(q[k]), lo2(p[k])); oq[k] = pack2(hi2(p[k]), lo2(q[k])); }
-              emit(y, op, oq);
-            }
-            return;
-          }
-          float4* const slot_a = ring0 + (S - 1) * kRingK + a_w;
-          float4* const slot_b = ring0 + (S - 1) * kRingK + o_n;
-          sts2(slot_a + 0 * 32, p[0], q[0]);
-          sts2(slot_a + 1 * 32, p[1], q[1]);
-          sts2(slot_a + 2 * 32, p[3], q[3]);
-          sts2(slot_b + 0 * 32, p[2], q[2]);
-          sts2(slot_b + 1 * 32, p[5], q[5]);
-          sts2(slot_b + 2 * 32, p[6], q[6]);
-          kp[0] = p[4]; kq[0] = q[4]; kp[1] = p[7]; kq[1] = q[7]; kp[2] = p[8]; kq[2] = q[8];
-        };
-        if (!any_blocked && !fold) finish(collide_quad_fast<ODD>(p, q, a.c));
-        else finish(collide_quad_generic<ODD>(p, q, bits, a.c, fold));
-        return word_next;
-      };
-
-      // Walk: iteration r runs step s on row r-(s-1), s = 1..K, as far as that row belongs to the step's range
-      // [yb-(K-s), ye+(K-s)); every range ends exactly with the last iteration.  The copies run D rows ahead;
-      // W[j] = obstacle word of row r+D-1-j, so step s reads W[D-2+s].
-      const int r0 = yb - (K - 1), r_last = ye + K - 2;
-      constexpr int NW = K + D - 1;
-      unsigned W[NW];
-#pragma unroll
-      for (int j = 0; j < NW; j++) W[j] = 0u;
-      W[D - 1] = issue();
-      if (D == 2 && r0 + 1 <= r_last) W[0] = issue();
-#pragma unroll 1
-      for (int r = r0; r <= r_last; r++) {
-        const unsigned w_new = step(std::integral_constant<int, 1>{}, r, W[D - 1], r + D <= r_last, r + 1 <= r_last);
-        if constexpr (K >= 2) { if (r >= yb - K + 3) step(std::integral_constant<int, 2>{}, r - 1, W[D], false, false); }
-        if constexpr (K >= 3) { if (r >= yb - K + 5) step(std::integral_constant<int, 3>{}, r - 2, W[D + 1], false, false); }
-        if constexpr (K >= 4) { if (r >= yb - K + 7) step(std::integral_constant<int, 4>{}, r - 3, W[D + 2], false, false); }
-        // (here, not inside the last step: its two halo lanes leave early, and the flag store is lane 0's)
-        if (r - (K - 1) >= yb) publish(r - (K - 1));
-        const int t = o_s; o_s = o_c; o_c = o_n; o_n = t;
-        const int u = a_w; a_w = a_r; a_r = u;
-#pragma unroll
-        for (int j = NW - 1; j >= 1; j--) W[j] = W[j - 1];
-        W[0] = w_new;
-      }
-    };
-    if (PEER && (band == 0 || band == g.bands - 1)) run_item(std::true_type{});
-    else run_item(std::false_type{});
+      for (int i = 0; i < K; i++) acc[i] += s.v[i];
+    } else {
+      stepsk_item<K, D, HINT, false>(a, g, band, strip, ring0, stage0, lane, acc);
+    }
   }
 
 #pragma unroll
