@@ -329,8 +329,8 @@ def bench_ours(args, pkg):
     nx, n = args.nx, world
     ips, K, W = args.timesteps, args.steps, args.warmup
     tuning_keys = ("kernel", "graph_steps", "ctas_per_sm", "min_ctas", "fused2", "fused_steps", "band_rows", "prefetch_rows",
-                   "cache_hint", "fused_deep")
-    pingpong_only = ("kernel", "min_ctas", "fused2", "fused_steps", "band_rows", "prefetch_rows", "fused_deep")
+                   "cache_hint", "fused_deep", "fused_ctas", "fused_k7")
+    pingpong_only = ("kernel", "min_ctas", "fused2", "fused_steps", "band_rows", "prefetch_rows", "fused_deep", "fused_ctas", "fused_k7")
 
     def make_sim(obstacles, fmt, rows, first, ny_global, ranks=n, inv=None):
         """One slab per rank on the CUDA IPC ring (ranks > 1) or the whole grid on this GPU, tuned as asked."""
@@ -601,6 +601,8 @@ def main():
                     help="two timesteps per pass over HBM: 1 on, 0 off, default automatic (on from 2^22 cells per GPU)")
     ap.add_argument("--fused-steps", dest="fused_steps", type=int, default=None, choices=[0, 2, 3, 4],
                     help="timesteps per pass over HBM of the fused kernel (2 = kernel 5, 3 or 4 = kernel 7)")
+    ap.add_argument("--fused-k7", dest="fused_k7", type=int, default=None, help="1 = kernel 7 also for two timesteps per pass")
+    ap.add_argument("--fused-ctas", dest="fused_ctas", type=int, default=None, help="kernel 7: CTAs per SM (0 = automatic)")
     ap.add_argument("--band-rows", dest="band_rows", type=int, default=None)
     ap.add_argument("--prefetch-rows", dest="prefetch_rows", type=int, default=None, help="kernel 5: L2 prefetch distance in rows")
     ap.add_argument("--cache-hint", dest="cache_hint", type=int, default=None)

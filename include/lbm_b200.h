@@ -192,8 +192,8 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
  *                   On a multi-process ring set it on every rank while the ring is idle.
  *   "fused_steps"   timesteps per pass over HBM where "fused2" is in use: 2 = kernel 5; 3 or 4 = kernel 7 (a chain
  *                   of shared-memory rings, one per intermediate step; a third / a quarter of the DRAM traffic per
- *                   step; ring slabs keep four halo rows per side and need >= 6 rows each); 0 = automatic (4 from
- *                   2^26 cells per GPU, 3 from 2^25, else 2).  Reads back the number in use (1 without "fused2").
+ *                   step; ring slabs keep four halo rows per side and need >= 6 rows each -- thinner ones fall back to
+ *                   kernel 5); 0 = automatic (3).  Reads back the number in use (1 without "fused2").
  *                   Runs whose length is not a multiple end with a shorter pass through the same kernel.
  *   "cluster"       kernel 6: the whole grid resident in the shared memory of ONE 16-CTA thread-block cluster for up
  *                   to 256 timesteps per launch, halo rows read from the neighbour CTA over distributed shared

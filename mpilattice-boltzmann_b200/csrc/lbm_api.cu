@@ -125,6 +125,8 @@ struct lbm_b200 {
   long opt_staging_bytes = (long)kBounceBytes;
   long opt_kernel = 0, opt_graph_steps = -1, opt_ctas_per_sm = 0, opt_min_ctas = 2, opt_cache_hint = 0, opt_resident = -1;
   long opt_fused2 = -1, opt_band_rows = 0;   // -1 / 0 = automatic
+  long opt_fused_k7 = 0;                // 1 = kernel 7 also for two timesteps per pass (instead of kernel 5)
+  long opt_fused_ctas = 0;              // kernel 7: CTAs per SM its resident warps are split into (0 = automatic)
   long opt_cluster = -1;                // kernel 6: -1 automatic, 0 never, 1 wherever it fits
   long opt_fused_steps = 0;             // timesteps per pass over HBM of the fused kernel: 2 = kernel 5, 3 or 4 = kernel 7,
                                         // 0 = automatic (fused_steps_wanted)
@@ -294,9 +296,12 @@ int stage_rows(const lbm_b200* h)
   return h->fusedk ? 1 : 2;
 }
 
-// Launch shape of kernel 7 for k steps per pass and d staging rows: warps per CTA x CTAs per SM = the warps whose
-// rings and staging rows fit into an SM's shared memory (lbm::stepsk_max_warps).
-void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm)
+// Launch shape of kernel 7 for k steps per pass and d staging rows.  Default: ONE warp per CTA, as many CTAs per SM
+// as fit into its shared memory (a CTA costs 1 KB + the 256 static bytes on top of its warp's rings and staging rows)
+// and its register file (12 x 32 x 168) -- an SM slot is free again the moment a work item ends.  Against CTAs of
+// 4 or 11 warps: +3.5 % at 16384^2 and +8.5 % on a 16384 x 2048 slab (K = 3, profiles/r02_fused2.md).  want_ctas > 0
+// (option "fused_ctas") splits the warps that fit by shared memory alone into that many CTAs instead.
+void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm, int want_ctas = 0)
 {
   auto max_warps = [&]() {
     switch (k * 10 + d) {
@@ -307,10 +312,14 @@ void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm)
     }
   };
   const int w = max_warps();
-  int ctas = 1;
-  for (int c : {3, 2}) if (w % c == 0) { ctas = c; break; }   // small CTAs where the count divides: finer scheduling
-  *ctas_per_sm = ctas;
-  *warps_per_cta = w / ctas;
+  if (want_ctas > 0 && w % want_ctas == 0) {
+    *ctas_per_sm = want_ctas;
+    *warps_per_cta = w / want_ctas;
+    return;
+  }
+  const size_t per_cta = (size_t)lbm::stepsk_warp_float4(k, d) * 16 + 1024 + 256;
+  *warps_per_cta = 1;
+  *ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, 232448 / per_cta));
 }
 
 // Padded rows of a plane beyond the slab's own: lbm::kHalo halo rows per side.  Rows 0 and rows+1 are the ones next to
@@ -328,20 +337,18 @@ int y_of_padded(int rows, int r)
 }
 
 // Kernel 7 (K = 3 or 4 timesteps per pass) where kernel 5 applies, K was asked for and the rows allow it.
-// Timesteps per pass of the fused kernel.  Automatic (profiles/r02_fused2.md, one B200): kernel 7 needs 19..28 KB of
-// shared memory per warp, so only 8..11 warps are resident per SM and a pass has fewer, longer work items; it wins
-// from 2^26 cells per GPU with K = 4 (8192^2: 167.7 vs 156.6 GLUPS, 16384^2: 176.6 vs 157.9), by 2 % with K = 3 at
-// 2^25 (16384 x 2048), and loses below (4096^2: 105..119 vs 143).
+// Timesteps per pass of the fused kernel.  Automatic: 3 (kernel 7 with one staging row, ten one-warp CTAs per SM)
+// wherever a fused kernel runs -- one B200, GLUPS for K = 2 (kernel 5) / 3 / 4: 2048^2 120.7 / 124.7 / 95.7, 4096^2
+// 143.2 / 145.7 / 105.7, 8192^2 157.8 / 172.0 / 167.5, 16384 x 2048 151.4 / 165.7 / 152.8, 16384^2 157.9 / 180.2 /
+// 176.6 (profiles/r02_fused2.md).
 int fused_steps_wanted(const lbm_b200* h)
 {
-  if (h->opt_fused_steps != 0) return (int)h->opt_fused_steps;
-  const long cells = (long)h->nx * h->ny / h->n_ranks;
-  return cells >= (1L << 26) ? 4 : (cells >= (1L << 25) ? 3 : 2);
+  return h->opt_fused_steps != 0 ? (int)h->opt_fused_steps : 3;
 }
 
 bool want_fusedk(const lbm_b200* h)
 {
-  if (fused_steps_wanted(h) < 3) return false;
+  if (fused_steps_wanted(h) < 3 && !h->opt_fused_k7) return false;
   if (h->n_ranks == 1) return h->ny >= 2 * lbm::kHalo;
   // a ring: every slab holds its neighbours' kHalo rows, and the driven row ny-2 must not be a row a slab other than
   // the one north of its owner recomputes (a whole-domain handle sees all slabs, a one-slab-per-process handle its
@@ -402,7 +409,7 @@ void plan(lbm_b200* h)
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
       int bands = 1, per = s.rows;
       int k7_wpc = 0, k7_ctas = 0;
-      if (h->fusedk) stepsk_shape(h->fusedk, stage_rows(h), &k7_wpc, &k7_ctas);
+      if (h->fusedk) stepsk_shape(h->fusedk, stage_rows(h), &k7_wpc, &k7_ctas, (int)h->opt_fused_ctas);
       const int resident_warps = h->fusedk ? k7_wpc * k7_ctas : (stage_rows(h) == 2 ? 12 : 16);
       plan_bands_k(s.rows, h->nx, (int)h->opt_band_rows, sms, h->fusedk ? h->fusedk : 2, resident_warps, h->n_ranks > 1, &bands, &per);
       s.fused_bands = bands;
@@ -869,7 +876,7 @@ template <int K, int D, bool PEER>
 int launch_stepsk(lbm_b200* h, Slab& s, const StepArgs& a, const lbm::StepsKArgs& g)
 {
   int wpc = 0, ctas = 0;
-  stepsk_shape(K, D, &wpc, &ctas);
+  stepsk_shape(K, D, &wpc, &ctas, K == h->fusedk ? (int)h->opt_fused_ctas : 0);
   const size_t smem = (size_t)wpc * lbm::stepsk_warp_bytes(K, D);
   auto kernel = lbm::steps_strip<K, D, 0, PEER>;
   const unsigned bit = 1u << (2 * K + D + (PEER ? 16 : 0));
@@ -1872,6 +1879,12 @@ int lbm_b200_set_option(lbm_b200* h, const char* key, long value)
   } else if (!strcmp(key, "cluster")) {
     if (value < -1 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster must be -1, 0 or 1");
     h->opt_cluster = value;
+  } else if (!strcmp(key, "fused_k7")) {
+    if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "fused_k7 must be 0 or 1");
+    h->opt_fused_k7 = value;
+  } else if (!strcmp(key, "fused_ctas")) {
+    if (value < 0 || value > 12) return fail(LBM_B200_ERR_ARG, "fused_ctas must be 0 (automatic) .. 12");
+    h->opt_fused_ctas = value;
   } else if (!strcmp(key, "cluster_rows")) {
     if (value < 0 || value > 1) return fail(LBM_B200_ERR_ARG, "cluster_rows must be 0 or 1");
     h->opt_cluster_rows = value;
@@ -1925,6 +1938,8 @@ int lbm_b200_get_option(const lbm_b200* h, const char* key, long* value)
   if (!strcmp(key, "kernel")) *value = h->inplace ? 4 : (h->cluster ? 6 : (h->fused2 ? (h->fusedk ? 7 : 5) : (h->resident ? 3 : (use_vec4(h) ? 2 : 1))));
   else if (!strcmp(key, "fused_steps")) *value = h->fused2 ? (h->fusedk ? h->fusedk : 2) : 1;
   else if (!strcmp(key, "cluster")) *value = h->cluster ? 1 : 0;
+  else if (!strcmp(key, "fused_ctas")) *value = h->opt_fused_ctas;
+  else if (!strcmp(key, "fused_k7")) *value = h->opt_fused_k7;
   else if (!strcmp(key, "cluster_rows")) *value = (h->cluster && h->cluster_rows) ? 1 : 0;
   else if (!strcmp(key, "fused2")) *value = h->fused2 ? 1 : 0;
   else if (!strcmp(key, "band_rows")) *value = h->fused2 ? h->slabs[0].fused_band_rows : h->opt_band_rows;

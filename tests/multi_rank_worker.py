@@ -34,6 +34,7 @@ def main(out_path):
     sim.connect_ipc(blobs[(rank - 1) % size], blobs[(rank + 1) % size])
     if os.environ.get("LBM_TEST_FUSED2") == "1":
         sim.set_option("band_rows", 8)
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") == 5
         if os.environ.get("LBM_TEST_FUSED_STEPS"):

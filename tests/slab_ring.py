@@ -217,6 +217,67 @@ def run_slab_fused2(pkg, oracle, rank, size, nx, ny, iters, density, accel, omeg
     return a[2:R + 2].copy(), av
 
 
+# ---- K timesteps per pass on a ring (csrc/lbm_stepsk.cuh kernel 7): four halo rows per side, one exchange per pass ----
+def run_slab_fusedk(pkg, oracle, rank, size, nx, ny, iters, density, accel, omega, obstacles, cells0, steps=4):
+    """Kernel 7's ring protocol with the oracle's stepper: a slab keeps H = 4 halo rows per side (all nine planes); in a
+    pass of k <= `steps` timesteps, step s is computed for the rows [-(k-s), R+(k-s)) -- the neighbours' rows out of the
+    halo rows, redundantly --, step k for the slab's own rows only; then the slab's first and last four rows go into
+    the neighbours' halo rows.  Halo rows a pass does not recompute are NaN afterwards: a pull of anything that was not
+    exchanged would show.  The body force of the step that comes next is applied to the driven row by its owner and --
+    while the steps still recompute it -- to the copy the slab north of the owner holds as its row -2.
+    Array rows: index i <-> slab row i-4."""
+    H = 4
+    rows_all, first_all = pkg.decompose(ny, size)
+    R, first = int(rows_all[rank]), int(first_all[rank])
+    assert min(int(r) for r in rows_all) >= H + 2
+    inv = pkg.free_cells_inv(obstacles)
+    gy = [(first + i - H) % ny for i in range(R + 2 * H)]
+    ob = np.ascontiguousarray(obstacles[gy])
+    a = np.full((R + 2 * H, nx, 9), np.nan, np.float32)
+    a[H:R + H] = cells0[first:first + R]
+    accel_i = (ny - 2 - first) + H if first <= ny - 2 < first + R else -1      # array index of the driven row, if owned
+    copy_i = H - 2 if first == 0 and size > 1 else -1                           # rank 0's copy of it: row -2
+    av = np.zeros(iters, np.float32)
+
+    def exchange(state):
+        up = np.stack([state[H + R - d] for d in range(1, H + 1)])              # rows R-1 .. R-4 go north
+        down = np.stack([state[H + d - 1] for d in range(1, H + 1)])            # rows 0 .. 3 go south
+        from_south, from_north = swap_rows(up, down, rank, size)
+        for d in range(1, H + 1):
+            state[H - d] = from_south[d - 1]                                    # the southern slab's d-th row from its end
+            state[H + R + d - 1] = from_north[d - 1]                            # the northern slab's d-th row
+
+    def force(state, i):
+        vals = np.ascontiguousarray(state[i])
+        oracle.accelerate_row(vals, ob[i], density, accel)
+        state[i] = vals
+
+    exchange(a)
+    t = 0
+    while t < iters:
+        k = min(steps, iters - t)
+        cur = a
+        for s in range(1, k + 1):
+            if accel_i > 0:
+                force(cur, accel_i)
+            if copy_i >= 0 and s <= k - 1:                       # row -1 of step s pulls from the forced row -2
+                force(cur, copy_i)
+            nxt = np.full_like(cur, np.nan)
+            lo, hi = H - (k - s), H + R + (k - s)
+            if lo < H:
+                oracle.slab_timestep(cur, nxt, ob, lo, H, omega)
+            av[t + s - 1] = oracle.slab_timestep(cur, nxt, ob, H, H + R, omega) * inv   # only the own rows count
+            if hi > H + R:
+                oracle.slab_timestep(cur, nxt, ob, H + R, hi, omega)
+            cur = nxt
+        a = cur
+        a[:H] = np.nan
+        a[H + R:] = np.nan
+        exchange(a)
+        t += k
+    return a[H:R + H].copy(), av
+
+
 def worker(rank, size, port, args, out_queue, inplace=False):
     import os
     import sys
@@ -231,7 +292,8 @@ def worker(rank, size, port, args, out_queue, inplace=False):
     pkg = entry.load_package()
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
-        runner = {False: run_slab, True: run_slab_inplace, "fused2": run_slab_fused2}[inplace]
+        runner = {False: run_slab, True: run_slab_inplace, "fused2": run_slab_fused2,
+                  "fused3": lambda *a: run_slab_fusedk(*a, steps=3), "fused4": lambda *a: run_slab_fusedk(*a, steps=4)}[inplace]
         cells, av = runner(pkg, oracle_lib, rank, size, *args)
         # the final reduction of the per-rank av_vels arrays (reference d2q9-bgk.c:396)
         total = torch.from_numpy(av.copy())

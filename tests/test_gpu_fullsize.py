@@ -56,9 +56,9 @@ def test_full_size_inplace(pkg, oracle):
 
 @pytest.mark.parametrize("steps", [2, 0])
 def test_full_size_fused(pkg, oracle, steps):
-    """Two timesteps per pass (kernel 5) and the automatic choice at this size (kernel 7, four per pass) at 16384 x
-    16384 (137 strips of 120 columns -- the last one 64 wide): 7 steps = three passes of two and a single-step tail, or
-    one pass of four and one of three, against the tiled 128-wide oracle."""
+    """Two timesteps per pass (kernel 5) and the automatic choice (kernel 7, three per pass) at 16384 x 16384 (137
+    strips of 120 columns -- the last one 64 wide): 7 steps = three passes of two and a single-step tail, or two
+    passes of three and one of one, against the tiled 128-wide oracle."""
     period, iters = 128, 7
     rng = np.random.default_rng(44)
     narrow = narrow_pattern(period, rng)
@@ -69,7 +69,7 @@ def test_full_size_fused(pkg, oracle, steps):
     with pkg.Simulation(NX, NY, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         sim.set_option("fused2", 1)
         sim.set_option("fused_steps", steps)
-        assert (sim.get_option("kernel"), sim.get_option("fused_steps")) == ((5, 2) if steps == 2 else (7, 4))
+        assert (sim.get_option("kernel"), sim.get_option("fused_steps")) == ((5, 2) if steps == 2 else (7, 3))
         av = sim.run(iters)
         assert sim.get_option("launches") < 12
         for got, want in zip(sim.final_state(), ref_fields):

@@ -51,6 +51,7 @@ def test_fused2_across_devices(pkg, oracle, n):
     ref_av = oracle.run(ref, obstacles, iters + 30, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n) as sim:
         sim.set_option("band_rows", 4)
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") == 5
         sim.set_cells(cells0)

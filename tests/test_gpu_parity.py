@@ -395,6 +395,7 @@ def test_fused2_bit_exact(pkg, oracle, nx, ny, band, iters):
     cells0[ny - 2, : nx // 3, 3] = 1e-5
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
         sim.set_option("band_rows", band)                       # 0 = automatic
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         if nx == 4096:
             sim.set_option("ctas_per_sm", 1)                    # fewer CTAs than work items: the item loop strides
@@ -411,6 +412,7 @@ def test_fused2_runs_compose_and_match_the_single_step_kernel(pkg, oracle):
     cells0 = random_cells(rng, ny, nx)
     ref_cells, ref_av, ref_exact = oracle_run(oracle, pkg, cells0, obstacles, 13)
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles) as sim:
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         sim.set_option("band_rows", 16)
         sim.set_cells(cells0)
@@ -424,6 +426,7 @@ def test_fused2_runs_compose_and_match_the_single_step_kernel(pkg, oracle):
 def test_fused2_is_refused_where_it_does_not_apply(pkg):
     ob = np.zeros((12, 128), np.int32)
     with pkg.Simulation(128, 12, DENSITY, ACCEL, OMEGA, ob) as sim:     # narrower than two strips: stays on kernel 2
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") != 5 and sim.get_option("fused2") == 0
 
@@ -444,6 +447,7 @@ def test_fused2_ring_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny,
     cells0[ny - 2, : nx // 3, 3] = 1e-5
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=n_slabs, devices=[0] * n_slabs) as sim:
         sim.set_option("band_rows", band)
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         assert sim.get_option("kernel") == 5
         sim.set_cells(cells0)
@@ -460,6 +464,7 @@ def test_fused2_ring_slabs_on_one_device_bit_exact(pkg, oracle, n_slabs, nx, ny,
         oracle.run(ref3, obstacles, 3, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
         sim.run(3)
         assert np.array_equal(bits(sim.get_cells()), bits(ref3))
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)                          # and on again: the two halo rows per side are fetched afresh
         oracle.run(ref3, obstacles, 4, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
         sim.run(4)

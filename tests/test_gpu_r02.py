@@ -89,6 +89,7 @@ def test_back_to_back_runs_on_a_fused_ring(pkg, oracle):
     oracle.run(ref, obstacles, 7 + 6 + 5 + 2, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, n_slabs=4, device=0) as sim:
         sim.set_option("band_rows", 4)
+        sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
         sim.set_option("fused2", 1)
         for it in (7, 6, 5, 2):
             sim.enqueue(it)
@@ -96,16 +97,19 @@ def test_back_to_back_runs_on_a_fused_ring(pkg, oracle):
         assert np.array_equal(bits(sim.get_cells()), bits(ref))
 
 
+@pytest.mark.parametrize("steps", [2, 0])
 @pytest.mark.parametrize("n", [1, 2, 4, 8])
-def test_bench_parity_case_on_one_device(pkg, n):
+def test_bench_parity_case_on_one_device(pkg, n, steps):
     """What bench.py checks before its timed region, here with the N slabs of a whole-domain handle on one device:
-    the committed expectation (tests/golden/ring_parity.npz) is met bit for bit by the two-steps-per-pass kernel."""
+    the committed expectation (tests/golden/ring_parity.npz) is met bit for bit by the two-steps-per-pass kernel and
+    by the automatic choice (kernel 7, three steps per pass)."""
     par = pkg.parity
     nx, ny = 256, par.ROWS_PER_RANK * n
     ob = par.obstacles(nx, ny, n)
     with pkg.Simulation(nx, ny, par.DENSITY, par.ACCEL, par.OMEGA, ob, n_slabs=n, device=0) as sim:
+        sim.set_option("fused_steps", steps)
         sim.set_option("fused2", 1)
-        assert sim.get_option("kernel") == 5
+        assert (sim.get_option("kernel"), sim.get_option("fused_steps")) == ((5, 2) if steps == 2 else (7, 3))
         for it in par.RUNS:
             sim.enqueue(it)
         sim.sync()
@@ -139,6 +143,7 @@ def test_fused_deep_variant_is_bit_identical(pkg, oracle, iters):
     ref_av = oracle.run(ref, obstacles, iters, DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     for band in (0, 5):
         with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
+            sim.set_option("fused_steps", 2)                     # kernel 5 (the automatic choice is kernel 7, K = 3)
             sim.set_option("fused2", 1)
             sim.set_option("fused_deep", 1)
             sim.set_option("band_rows", band)

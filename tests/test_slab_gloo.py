@@ -20,11 +20,14 @@ def free_port():
 
 @pytest.mark.parametrize("size,nx,ny,inplace,iters", [(2, 32, 24, False, 25), (2, 40, 17, False, 25), (3, 16, 19, False, 25),
                                                       (2, 32, 24, True, 12), (2, 40, 17, True, 13), (3, 16, 19, True, 9),
-                                                      (2, 32, 24, "fused2", 12), (2, 40, 17, "fused2", 13), (3, 16, 19, "fused2", 9)])
+                                                      (2, 32, 24, "fused2", 12), (2, 40, 17, "fused2", 13), (3, 16, 19, "fused2", 9),
+                                                      (2, 32, 24, "fused3", 13), (2, 40, 17, "fused4", 14), (3, 16, 25, "fused4", 11)])
 def test_slab_ring_matches_single_domain(pkg, oracle, size, nx, ny, inplace, iters):
     """inplace: the one-buffer (AA access pattern) ring protocol -- what crosses the slabs in which step flavour --
     ending in either layout.  "fused2": two timesteps per pass with two halo rows per side, only the planes the product
-    pushes (everything else in the halo rows is NaN), the driven row's copy on rank 0, an odd one-step tail."""
+    pushes (everything else in the halo rows is NaN), the driven row's copy on rank 0, an odd one-step tail.  "fused3" /
+    "fused4": kernel 7's protocol -- four halo rows per side, the steps before the last recomputed for the neighbours'
+    rows, the driven row's copy forced while it is still recomputed, shorter last passes."""
     rng = np.random.default_rng(size * 1000 + ny)
     density, accel, omega = 0.1, 0.005, 1.85
     obstacles = random_obstacles(rng, ny, nx, 0.08, walls=(ny % 2 == 0))   # odd ny: open top/bottom, y-wrap in play
