@@ -260,13 +260,13 @@ def peak_hbm():
 
 def kernel_source_hash(kernel=None) -> str:
     """sha256 over the sources of one kernel: profiles/roofline_traffic.json records the hash its ncu captures were
-    taken at.  Kernel 7 lives in lbm_stepsk.cuh (on top of the helpers in lbm_kernels.cuh), the others do not see it."""
+    taken at.  Kernel 7 lives in lbm_stepsk.cuh on top of the helpers in lbm_kernels.cuh and the arithmetic in
+    lbm_cell.cuh; the other timed kernels (2, 4, 5) are in lbm_kernels.cuh."""
     h = hashlib.sha256()
-    for path in sorted(glob.glob(os.path.join(ROOT, "mpilattice-boltzmann_b200", "csrc", "*.cuh"))):
-        if os.path.basename(path) == "lbm_stepsk.cuh" and str(kernel) != "7":
-            continue
-        h.update(os.path.basename(path).encode())
-        h.update(open(path, "rb").read())
+    files = ["lbm_cell.cuh", "lbm_kernels.cuh"] + (["lbm_stepsk.cuh"] if str(kernel) == "7" else [])
+    for name in files:
+        h.update(name.encode())
+        h.update(open(os.path.join(ROOT, "mpilattice-boltzmann_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 
 

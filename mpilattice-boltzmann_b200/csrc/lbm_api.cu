@@ -22,6 +22,7 @@
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
 #include "lbm_stepsk.cuh"
+#include "lbm_cluster.cuh"
 
 namespace {
 
@@ -83,6 +84,7 @@ struct Slab {
   int threads_int = 256, grid_int = 0;
   int per_step = 1;
   int fused_grid = 0, fused_bands = 0, fused_band_rows = 0;   // two-steps-per-pass kernel (kernel 5)
+  int fused_partials = 0;                // partial sums per step the fused kernel in use writes
   unsigned fusedk_attr = 0;              // kernel 7: bit 2K+D set once steps_strip<K, D> has its shared-memory opt-in on this device
   bool fused_attr = false;              // its dynamic shared memory opt-in has been made on this slab's device
   std::vector<cudaGraphExec_t> graphs;  // [parity]
@@ -297,10 +299,10 @@ int stage_rows(const lbm_b200* h)
 }
 
 // Launch shape of kernel 7 for k steps per pass and d staging rows.  Default: ONE warp per CTA, as many CTAs per SM
-// as fit into its shared memory (a CTA costs 1 KB + the 256 static bytes on top of its warp's rings and staging rows)
-// and its register file (12 x 32 x 168) -- an SM slot is free again the moment a work item ends.  Against CTAs of
-// 4 or 11 warps: +3.5 % at 16384^2 and +8.5 % on a 16384 x 2048 slab (K = 3, profiles/r02_fused2.md).  want_ctas > 0
-// (option "fused_ctas") splits the warps that fit by shared memory alone into that many CTAs instead.
+// as fit into its shared memory (a CTA costs 1 KB on top of its warp's rings and staging rows) and its register file
+// (12 x 32 x 168) -- an SM slot is free again the moment a work item ends.  Against CTAs of 4 or 11 warps: +3.5 % at
+// 16384^2 and +8.5 % on a 16384 x 2048 slab (K = 3, profiles/r02_fused2.md).  want_ctas > 0 (option "fused_ctas")
+// splits those warps into that many CTAs instead.
 void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm, int want_ctas = 0)
 {
   auto max_warps = [&]() {
@@ -312,14 +314,9 @@ void stepsk_shape(int k, int d, int* warps_per_cta, int* ctas_per_sm, int want_c
     }
   };
   const int w = max_warps();
-  if (want_ctas > 0 && w % want_ctas == 0) {
-    *ctas_per_sm = want_ctas;
-    *warps_per_cta = w / want_ctas;
-    return;
-  }
-  const size_t per_cta = (size_t)lbm::stepsk_warp_float4(k, d) * 16 + 1024 + 256;
-  *warps_per_cta = 1;
-  *ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, 232448 / per_cta));
+  const bool split = want_ctas > 0 && w % want_ctas == 0;
+  *ctas_per_sm = split ? want_ctas : w;
+  *warps_per_cta = split ? w / want_ctas : 1;
 }
 
 // Padded rows of a plane beyond the slab's own: lbm::kHalo halo rows per side.  Rows 0 and rows+1 are the ones next to
@@ -417,6 +414,7 @@ void plan(lbm_b200* h)
       const long items = (long)h->fused_strips * bands;
       const int wpc = h->fusedk ? k7_wpc : fused_warps(stage_rows(h) == 2);
       s.fused_grid = (int)std::min<long>((items + wpc - 1) / wpc, 1L << 30);
+      s.fused_partials = h->fusedk ? (int)std::min<long>((long)s.fused_grid * wpc, 1L << 30) : s.fused_grid;   // kernel 7: one per warp
       if (h->opt_ctas_per_sm > 0) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
@@ -428,13 +426,13 @@ void plan(lbm_b200* h)
     if (h->n_ranks == 1) {
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full, h->resident);
       s.grid_edge = s.grid_int = 0;
-      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_grid : 0);
+      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_partials : 0);
       if (h->cluster) s.per_step = std::max(s.per_step, lbm::kClusterCtas * (h->cluster_threads / 32));
     } else if (use_vec4(h)) {
       // one launch per step and slab: edge rows first, then the interior (csrc/lbm_kernels.cuh)
       plan_region(h, s.device, s.rows, &s.threads_full, &s.grid_full);
       s.grid_edge = s.grid_int = 0;
-      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_grid : 0);
+      s.per_step = std::max(s.grid_full, h->fused2 ? s.fused_partials : 0);
     } else {
       plan_region(h, s.device, 2, &s.threads_edge, &s.grid_edge);
       plan_region(h, s.device, s.rows - 2, &s.threads_int, &s.grid_int);
@@ -891,7 +889,7 @@ int launch_stepsk(lbm_b200* h, Slab& s, const StepArgs& a, const lbm::StepsKArgs
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
     grid = std::min<long>(grid, (long)sms * h->opt_ctas_per_sm);
   }
-  grid = std::min<long>(grid, s.per_step);                   // one partial per CTA and step
+  grid = std::min<long>(grid, s.per_step / wpc);             // one partial per warp and step
   kernel<<<dim3((unsigned)grid), dim3(wpc * 32), smem, s.stream>>>(a, g);
   CUDA_TRY(cudaGetLastError());
   return LBM_B200_OK;

@@ -3,17 +3,20 @@
 // One timestep = ONE pass over the slab: pull-stream (propagate), bounce-back (rebound), BGK
 // collision, next step's accelerate_flow on row ny-2, and the block-level partial of
 // Sigma |m|/rho -- replacing reference d2q9-bgk.c:345-367.  Populations are nine fp32 planes
-// (structure of arrays) of (rows+4) x nx floats: padded row 0 and rows+1 are the halo rows next to the
-// slab, rows+2 / rows+3 the second halo rows (kernel 5 on a ring), rows 1..rows are owned.  The
+// (structure of arrays) of (rows+8) x nx floats: padded row 0 and rows+1 are the halo rows next to the
+// slab, rows+2 .. rows+7 the neighbours' rows further away (kernels 5 and 7 on a ring), rows 1..rows are owned.  The
 // obstacle map is 1 bit per cell, 32 cells per word, rows padded to whole words.  Algorithmic
 // traffic: 9 loads + 9 stores = 72 B per cell per step (+1 bit).
 //
 //   kernel 1  step_scalar     one cell per thread, any nx
-//   kernel 2  step_vec4       one warp per 128-cell row segment, 128-bit accesses + shuffles (0.976 of copy peak)
+//   kernel 2  step_vec4       one warp per 128-cell row segment, 128-bit accesses + shuffles (0.989 of copy peak)
 //   kernel 3  steps_resident  kernel 2 in a cooperative many-steps-per-launch loop (launch-latency-bound grids)
 //   kernel 4  step_inplace    ONE buffer, AA access pattern (two alternating flavours)
-//   kernel 5  steps2_strip    TWO timesteps per pass over HBM through a shared-memory ring (default for big grids)
+//   kernel 5  steps2_strip    TWO timesteps per pass over HBM through a shared-memory ring
 //   kernel 6  steps_cluster   the grid resident in the shared memory of one 16-CTA cluster, halo rows over DSMEM
+//             (6b, steps_cluster_rows in lbm_cluster.cuh: one warp per 128-cell row -- the two smallest shipped decks)
+//   kernel 7  steps_strip     K = 1..4 timesteps per pass through K-1 rings (lbm_stepsk.cuh; K = 3 is the default for
+//             big grids)
 // Ring slabs (multi-GPU): halo rows are stored straight into the neighbours' buffers over NVLink by the
 // step kernels themselves; flag words (one per 128-cell chunk / 120-column strip) order the exchange.
 #pragma once
@@ -31,7 +34,7 @@ constexpr int kSegCells = 128;   // cells per warp work item in the vec4 kernel 
 struct StepArgs {
   const float* src;          // plane 0 of the source buffer
   float* dst;                // plane 0 of the destination buffer
-  size_t plane;              // floats between planes = (rows+4)*nx (two halo rows per side)
+  size_t plane;              // floats between planes = (rows+8)*nx (four halo rows per side)
   const uint32_t* mask;      // bit-packed obstacles of the owned rows, row r at (r-1)*mask_row_words
   int mask_row_words;
   int nx;
