@@ -229,8 +229,7 @@ size_t cluster_smem_bytes(const lbm_b200* h)
 {
   const size_t rows = (size_t)(h->ny / lbm::kClusterCtas);
   if (!h->cluster_rows) return 2 * 9 * sizeof(float) * rows * h->nx;
-  // + the steps' sums (laid out for the largest CTA) + four mbarriers
-  return 2 * 9 * sizeof(float) * (rows + 2) * h->nx + (size_t)kChunkSteps * lbm::kClusterMaxRows * sizeof(double) + 64;
+  return 2 * 9 * sizeof(float) * (rows + 2) * h->nx + (size_t)kChunkSteps * rows * sizeof(double);   // + the steps' sums
 }
 
 bool want_cluster(lbm_b200* h)

@@ -30,30 +30,6 @@ __device__ __forceinline__ void sts2_cluster(unsigned cluster_addr, f2 a, f2 b)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// Neighbour-to-neighbour ordering of the halo rows: an mbarrier in the RECEIVING CTA's shared memory, on which every
-// lane of the sending warp arrives (release, cluster scope) after its remote stores; the receiving warp waits for the
-// phase (acquire, cluster scope).  A step then costs one DSMEM round trip between neighbours instead of a barrier
-// (with its fences) across all sixteen CTAs.
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(unsigned cluster_bar)
-{
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
-}
-// (bounded: a neighbour that never arrives would otherwise hang the GPU until it is reset -- trap instead)
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-  for (unsigned spins = 0;; spins++) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-    if (spins > (1u << 24)) __trap();
-  }
-}
-
 constexpr int kClusterRowCells = 128;      // nx of kernel 6b
 constexpr int kClusterMaxRows = 16;        // rows per CTA: 16 warps x 128 registers fill the register file
 
@@ -74,9 +50,6 @@ __global__ void __launch_bounds__(MAXROWS * 32, 1) steps_cluster_rows(const Clus
   // (behind the two buffers: one double per step and row -- the step's share of Sigma |m|/rho stays on chip until the
   // launch ends, so that the barrier's release fence never waits for a store to global memory)
   double* const sums = reinterpret_cast<double*>(cluster_rows_smem + 2 * 9 * prow * 32);
-  // ... and four mbarriers: halo rows arrived from the south / from the north, one per buffer parity
-  const unsigned bars = (unsigned)__cvta_generic_to_shared(sums + 256 * kClusterMaxRows);
-  const unsigned from_south_bar = bars, from_north_bar = bars + 16;          // [2] each
   float4* const mine = cluster_rows_smem + lane;
   auto at = [&](int b, int k, int r) -> float4* { return mine + ((b * 9 + k) * prow + r) * 32; };
   const unsigned mine_s = (unsigned)__cvta_generic_to_shared(mine);
@@ -111,29 +84,15 @@ __global__ void __launch_bounds__(MAXROWS * 32, 1) steps_cluster_rows(const Clus
   // where this row's planes go in the neighbour CTAs' halo rows (first row: 4,7,8 south; last row: 2,5,6 north)
   const unsigned to_south = map_to_cta(mine_s, south) + (unsigned)((rows + 1) * 512);
   const unsigned to_north = map_to_cta(mine_s, north);
-  // my pushes south land in the southern CTA's "from the north" rows, and vice versa
-  const unsigned south_bar = map_to_cta(from_north_bar, south), north_bar = map_to_cta(from_south_bar, north);
-  if (threadIdx.x == 0) {
-    mbar_init(from_south_bar, 32); mbar_init(from_south_bar + 8, 32);
-    mbar_init(from_north_bar, 32); mbar_init(from_north_bar + 8, 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
-  cluster_arrive();                                             // every CTA of the cluster runs (and has its mbarriers)
-  cluster_wait();                                               // before anybody pushes
+  cluster_arrive();                                             // every CTA of the cluster runs before anybody pushes
+  cluster_wait();
 
 #pragma unroll 1
   for (int t = 0; t < a.steps; t++) {
     const int cur = t & 1, nxt = cur ^ 1;
     const bool rot = (cur == 0);                                // column order in, rotated out (and back in the next step)
     const bool fold = driven && ((t + 1 < a.steps) || a.fold_last);
-    if (t > 0) {
-      // the neighbours' pushes of step t-1 (they went into this step's source buffer) -- which also says that the
-      // neighbour is done reading the halo row this step's pushes overwrite
-      const unsigned b = (unsigned)((t - 1) & 1) * 8, parity = (unsigned)((t - 1) >> 1) & 1u;
-      if (row == 0) mbar_wait(from_south_bar + b, parity);
-      if (row == rows - 1) mbar_wait(from_north_bar + b, parity);
-    }
     f2 lo[9], hi[9];
     lds2(at(cur, 0, pr), lo[0], hi[0]); lds2(at(cur, 1, pr), lo[1], hi[1]); lds2(at(cur, 3, pr), lo[3], hi[3]);
     lds2(at(cur, 2, pr - 1), lo[2], hi[2]); lds2(at(cur, 5, pr - 1), lo[5], hi[5]); lds2(at(cur, 6, pr - 1), lo[6], hi[6]);
@@ -181,22 +140,20 @@ __global__ void __launch_bounds__(MAXROWS * 32, 1) steps_cluster_rows(const Clus
       sts2_cluster(to_south + (unsigned)((nxt * 9 + 4) * prow * 512), p[4], q[4]);
       sts2_cluster(to_south + (unsigned)((nxt * 9 + 7) * prow * 512), p[7], q[7]);
       sts2_cluster(to_south + (unsigned)((nxt * 9 + 8) * prow * 512), p[8], q[8]);
-      mbar_arrive_remote(south_bar + (unsigned)(t & 1) * 8);
     }
     if (row == rows - 1) {                                      // planes 2,5,6 -> the northern CTA's halo row 0
       sts2_cluster(to_north + (unsigned)((nxt * 9 + 2) * prow * 512), p[2], q[2]);
       sts2_cluster(to_north + (unsigned)((nxt * 9 + 5) * prow * 512), p[5], q[5]);
       sts2_cluster(to_north + (unsigned)((nxt * 9 + 6) * prow * 512), p[6], q[6]);
-      mbar_arrive_remote(north_bar + (unsigned)(t & 1) * 8);
     }
+    cluster_arrive();                                           // this warp's new row (and halo rows) are on their way
     double acc = (double)u4;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) sums[t * rows + row] = acc;
-    __syncthreads();                                            // the CTA's own rows of this step are complete
+    cluster_wait();                                             // ... and everybody's are visible
   }
-  cluster_arrive();                                             // nobody leaves while a neighbour may still push to it
-  cluster_wait();
+  __syncthreads();
   for (int i = threadIdx.x; i < a.steps * rows; i += blockDim.x)
     a.partials[(size_t)(i / rows) * a.partial_stride + rank * rows + (i % rows)] = sums[i];
 
