@@ -55,19 +55,42 @@ __host__ __device__ constexpr int stepsk_max_warps(int k, int d)
   return (int)(232448 / (stepsk_warp_bytes(k, d) + 1024)) > 12 ? 12 : (int)(232448 / (stepsk_warp_bytes(k, d) + 1024));
 }
 
-// One work item: the walk of one warp down one strip of one band.  EDGE (ring slabs only): the band touches the slab's
-// first or last row -- halo rows, flag handshake and pushes; every other band of a ring slab runs exactly the
-// single-GPU code.  acc[s] += the item's share of step s+1's Sigma |m|/rho.
-template <int K, int D, int HINT, bool EDGE>
-__device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs& g, const int band, const int strip,
+// The ring protocol's two calls, out of line: they run twice per EDGE item, and every instruction they would add to the
+// walk's body costs all items (unrolling the nine plane copies of a push inside the body: -1.7 % on every slab).
+__device__ __noinline__ void strip_wait_cold(const StepArgs& a, const unsigned* flags, unsigned dir, int strip, int strips, int lane)
+{
+  strip_wait(a, flags, dir, strip, strips, lane);
+}
+__device__ __noinline__ void strip_signal_cold(const StepArgs& a, unsigned* flags, int strip, int lane)
+{
+  strip_signal(a, flags, strip, lane);
+}
+
+// One work item: the walk of one warp down one strip of one band.  `edge` (ring slabs only, warp-uniform): the band
+// touches the slab's first or last row -- halo rows, flag handshake and pushes.  It is a RUN-TIME flag on one copy of
+// the walk: with the edge form as a second copy of the code (inlined, or out of line) the items of a pass's first
+// wave -- edge and interior items side by side on every SM -- fought over the instruction cache: same instruction
+// count, 12 % longer passes on 2048-row slabs (3.6 waves per pass), 2.8 % on 16384-row ones (ncu, profiles/
+// r02_fused2.md).  acc[s] += the item's share of step s+1's Sigma |m|/rho.
+template <int K, int D, int HINT, bool PEER>
+__device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs& g, const int band, const int strip, const bool edge,
                                             float4* const ring0, const float4* const stage0, const int lane, double (&acc)[K])
 {
+  const bool EDGE = PEER && edge;
   const unsigned stage0_s = (unsigned)__cvta_generic_to_shared(stage0);
+  // (everything the walk needs of the two argument structs, by value)
   const float* __restrict__ src = a.src;
   float* __restrict__ dst = a.dst;
   const size_t P = a.plane;
   const int rows = a.row_last;                               // owned padded rows are 1..rows
   const int nx = a.nx;
+  const StepConst c = a.c;
+  const int mask_row_words = a.mask_row_words;
+  const int band_rows = g.band_rows, bands = g.bands, strips = g.strips, accel_y = g.accel_y, fold_last = g.fold_last;
+  const int south_rows = g.south_rows, north_rows = g.north_rows;
+  float* const south_dst = a.south_dst;
+  float* const north_dst = a.north_dst;
+  const size_t south_plane = a.south_plane, north_plane = a.north_plane;
 
   // padded row of the 0-based row y in [-kHalo, rows+kHalo): halo rows at a ring slab's edges, periodic otherwise
   auto prow = [&](const int y) -> int {
@@ -89,8 +112,8 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
     if (EDGE || (unsigned)y < (unsigned)rows) return y;
     return (y < 0) ? y + rows : y - rows;
   };
-  const int yb = band * g.band_rows;                       // owned rows of the item, 0-based: [yb, ye)
-  const int ye = (band == g.bands - 1) ? rows : yb + g.band_rows;
+  const int yb = band * band_rows;                       // owned rows of the item, 0-based: [yb, ye)
+  const int ye = (band == bands - 1) ? rows : yb + band_rows;
   // this lane's aligned group of four columns (periodic): the strip's 120 owned columns are lanes 1..30
   int gx = strip * kStripOut - 4 + 4 * lane;
   if (gx < 0) gx += nx;
@@ -101,8 +124,8 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
 
   if (EDGE) {
     // the halo rows this item pulls (and the neighbour's halo columns it overwrites) are ordered by the flags
-    if (yb == 0) strip_wait(a, a.wait_from_south, kWaitFromSouth, strip, g.strips, lane);
-    if (ye == rows) strip_wait(a, a.wait_from_north, kWaitFromNorth, strip, g.strips, lane);
+    if (yb == 0) strip_wait_cold(a, a.wait_from_south, kWaitFromSouth, strip, strips, lane);
+    if (ye == rows) strip_wait_cold(a, a.wait_from_north, kWaitFromNorth, strip, strips, lane);
   }
 
   // ---- asynchronous copy of what the first step of row q_y pulls, into a staging row; returns the row's
@@ -126,39 +149,40 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
     cp_async16(stage_s + 8 * 512, pn + 8 * P);
     cp_async_commit();
     if (D == 2) stage_s ^= (stage0_s ^ (stage0_s + kStageSlot * 16));   // the other staging row next time
-    const unsigned word = __ldg(mask_x + (unsigned)mrow(q_y) * (unsigned)a.mask_row_words);   // used rows later
+    const unsigned word = __ldg(mask_x + (unsigned)mrow(q_y) * (unsigned)mask_row_words);   // used rows later
     q_y++;
     q_s = q_c; q_c = q_n; q_n = prow(q_y + 1);
     return word;
   };
 
-  // ---- a finished (owned) row y in column order: to the destination buffer and, on a ring, into the
-  //      neighbours' halo rows (all nine planes of the kHalo rows next to either edge) ----
+  // ---- a finished (owned) row y in column order: to the destination buffer ----
   auto emit = [&](const int y, const f2 (&p)[9], const f2 (&q)[9]) {
     float* const d = dst + ((unsigned)(y + 1) * (unsigned)nx + (unsigned)gx);
 #pragma unroll
     for (int k = 0; k < 9; k++) stg2<HINT>(d + k * P, p[k], q[k]);
-    if (EDGE) {
-      if (y < kHalo) {                                     // row y of this slab = row south_rows + y of the southern one
-        const int r = (y == 0) ? g.south_rows + 1 : g.south_rows + 2 * y + 1;
-        float* const t = a.south_dst + ((size_t)r * nx + gx);
-#pragma unroll
-        for (int k = 0; k < 9; k++) stg2<0>(t + k * a.south_plane, p[k], q[k]);
-      }
-      if (y >= rows - kHalo) {                             // = row y - rows of the northern one
-        const int dd = rows - y;                           // 1..kHalo
-        const int r = (dd == 1) ? 0 : g.north_rows + 2 * (dd - 1);
-        float* const t = a.north_dst + ((size_t)r * nx + gx);
-#pragma unroll
-        for (int k = 0; k < 9; k++) stg2<0>(t + k * a.north_plane, p[k], q[k]);
-      }
+  };
+  // ---- ring slabs: once the kHalo rows next to an edge are in the destination buffer, this lane copies its columns
+  //      of them (all nine planes) into the neighbour's halo rows over NVLink, and the warp publishes the strip.  A
+  //      rolled loop of loads (the lane's own stores of a moment ago) and stores: nothing of it sits in the walk's
+  //      straight-line code, whose instruction-cache footprint decides the speed of every item (see stepsk_item). ----
+  auto push_rows = [&](const int y0, const bool south) {
+    if (!owned) return;
+    float* const base = south ? south_dst : north_dst;
+    const size_t plane = south ? south_plane : north_plane;
+#pragma unroll 1
+    for (int y = y0; y < y0 + kHalo; y++) {
+      // row y of this slab is row south_rows + y of the southern slab / row y - rows of the northern one
+      const int r = south ? south_rows + 2 * y + 1 : (rows - y == 1 ? 0 : north_rows + 2 * (rows - y - 1));
+      const float* const from = dst + ((unsigned)(y + 1) * (unsigned)nx + (unsigned)gx);
+      float* const to = base + ((size_t)r * nx + gx);
+#pragma unroll 1
+      for (int k = 0; k < 9; k++) *reinterpret_cast<float4*>(to + k * plane) = __ldcg(reinterpret_cast<const float4*>(from + k * P));
     }
   };
-  // after the rows a neighbour waits for have been pushed: publish this strip (whole warp)
   auto publish = [&](const int y) {
     if (EDGE) {
-      if (y == kHalo - 1) strip_signal(a, a.signal_south, strip, lane);
-      if (y == rows - 1) strip_signal(a, a.signal_north, strip, lane);
+      if (y == kHalo - 1) { push_rows(0, true); strip_signal_cold(a, a.signal_south, strip, lane); }
+      if (y == rows - 1) { push_rows(rows - kHalo, false); strip_signal_cold(a, a.signal_north, strip, lane); }
     }
   };
 
@@ -204,7 +228,7 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
     const unsigned bits = (mword >> mask_shift) & 0xFu;
     const bool any_blocked = __any_sync(0xffffffffu, bits != 0u);
     if (LAST && !ODD && !owned) return word_next;
-    const bool fold = (LAST ? g.fold_last != 0 : true) && (ident(y) == g.accel_y);
+    const bool fold = (LAST ? fold_last != 0 : true) && (ident(y) == accel_y);
     f2 p[9], q[9];
     if (ODD) {                                             // p = cells (1,2), q = cells (3,0)
       p[0] = pack2(hi2(lo[0]), lo2(hi[0])); q[0] = pack2(hi2(hi[0]), lo2(lo[0]));
@@ -252,8 +276,8 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
       sts2(slot_b + 2 * 32, p[6], q[6]);
       kp[0] = p[4]; kq[0] = q[4]; kp[1] = p[7]; kq[1] = q[7]; kp[2] = p[8]; kq[2] = q[8];
     };
-    if (!any_blocked && !fold) finish(collide_quad_fast<ODD>(p, q, a.c));
-    else finish(collide_quad_generic<ODD>(p, q, bits, a.c, fold));
+    if (!any_blocked && !fold) finish(collide_quad_fast<ODD>(p, q, c));
+    else finish(collide_quad_generic<ODD>(p, q, bits, c, fold));
     return word_next;
   };
 
@@ -283,21 +307,6 @@ __device__ __forceinline__ void stepsk_item(const StepArgs& a, const StepsKArgs&
   }
 }
 
-// The edge items of a ring slab, out of line: with both forms inlined into one kernel body the INTERIOR items of a
-// ring slab ran 3 % slower than the single-GPU kernel (same box, 171.2 vs 177.1 GLUPS per 16384^2 slab,
-// profiles/r02_fused2.md) -- the hot loop's register allocation and layout paid for code it never runs.
-template <int K> struct StepSums { double v[K]; };
-template <int K, int D, int HINT>
-__device__ __noinline__ StepSums<K> stepsk_edge_item(const StepArgs& a, const StepsKArgs& g, const int band, const int strip,
-                                                      float4* const ring0, const float4* const stage0, const int lane)
-{
-  StepSums<K> s;
-#pragma unroll
-  for (int i = 0; i < K; i++) s.v[i] = 0.0;
-  stepsk_item<K, D, HINT, true>(a, g, band, strip, ring0, stage0, lane, s.v);
-  return s;
-}
-
 template <int K, int D, int HINT, bool PEER>
 __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(const StepArgs a, const StepsKArgs g)
 {
@@ -318,13 +327,7 @@ __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(co
     // a ring slab does its two edge bands first: their rows are on the way to the neighbours (and published) while
     // the interior bands run, as the reference overlaps its halo exchange with the interior rows (326-366)
     if (PEER && g.bands > 2) band = (band == 0) ? 0 : (band == 1 ? g.bands - 1 : band - 1);
-    if (PEER && (band == 0 || band == g.bands - 1)) {
-      const StepSums<K> s = stepsk_edge_item<K, D, HINT>(a, g, band, strip, ring0, stage0, lane);
-#pragma unroll
-      for (int i = 0; i < K; i++) acc[i] += s.v[i];
-    } else {
-      stepsk_item<K, D, HINT, false>(a, g, band, strip, ring0, stage0, lane, acc);
-    }
+    stepsk_item<K, D, HINT, PEER>(a, g, band, strip, PEER && (band == 0 || band == g.bands - 1), ring0, stage0, lane, acc);
   }
 
   // one partial per WARP and step (fixed tree, no shared memory: the 256 static bytes of block_sum_to would cost K = 3
@@ -336,7 +339,16 @@ __global__ void __launch_bounds__(stepsk_max_warps(K, D) * 32, 1) steps_strip(co
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) a.partials[(size_t)s * g.partial_stride + (size_t)blockIdx.x * warps + warp] = v;
   }
-  if (PEER) peer_advance_epoch(a);
+  // End of a ring launch: the last CTA to leave advances the slab's epoch.  No fence: the epoch is read by this slab's
+  // NEXT launch only (stream order), and the last CTA knows that every other one has left (with one-warp CTAs the
+  // fence of peer_advance_epoch sat at the end of every work item).
+  if (PEER && threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done = 0;
+      *reinterpret_cast<volatile unsigned*>(a.epoch) = *reinterpret_cast<volatile unsigned*>(a.epoch) + 1u;
+    }
+  }
 }
 
 }  // namespace lbm
