@@ -259,14 +259,18 @@ def peak_hbm():
 
 
 def kernel_source_hash(kernel=None) -> str:
-    """sha256 over the sources of one kernel: profiles/roofline_traffic.json records the hash its ncu captures were
-    taken at.  Kernel 7 lives in lbm_stepsk.cuh on top of the helpers in lbm_kernels.cuh and the arithmetic in
-    lbm_cell.cuh; the other timed kernels (2, 4, 5) are in lbm_kernels.cuh."""
+    """sha256 over the CODE of one kernel's sources (comments and white space stripped, so that a comment fix does not
+    disown a measurement): profiles/roofline_traffic.json records the hash its ncu captures were taken at.  Kernel 7
+    lives in lbm_stepsk.cuh on top of the helpers in lbm_kernels.cuh and the arithmetic in lbm_cell.cuh; the other
+    timed kernels (2, 4, 5) are in lbm_kernels.cuh."""
     h = hashlib.sha256()
     files = ["lbm_cell.cuh", "lbm_kernels.cuh"] + (["lbm_stepsk.cuh"] if str(kernel) == "7" else [])
     for name in files:
+        text = open(os.path.join(ROOT, "mpilattice-boltzmann_b200", "csrc", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)           # block comments
+        text = re.sub(r"//[^\n]*", "", text)                        # line comments (no string in these files holds "//")
         h.update(name.encode())
-        h.update(open(os.path.join(ROOT, "mpilattice-boltzmann_b200", "csrc", name), "rb").read())
+        h.update("".join(text.split()).encode())
     return h.hexdigest()[:16]
 
 

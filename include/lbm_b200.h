@@ -195,6 +195,9 @@ int lbm_b200_get_final_state(lbm_b200* handle, float* u_x, float* u_y, float* u,
  *                   step; ring slabs keep four halo rows per side and need >= 6 rows each -- thinner ones fall back to
  *                   kernel 5); 0 = automatic (3).  Reads back the number in use (1 without "fused2").
  *                   Runs whose length is not a multiple end with a shorter pass through the same kernel.
+ *   "fused_ctas"    kernel 7: CTAs per SM its resident warps are grouped into (0 = automatic: one warp per CTA, so that
+ *                   an SM slot is free again the moment a work item ends; other values are for A/B measurements)
+ *   "fused_k7"      1 = kernel 7 also for "fused_steps" = 2 (default 0: kernel 5)
  *   "cluster"       kernel 6: the whole grid resident in the shared memory of ONE 16-CTA thread-block cluster for up
  *                   to 256 timesteps per launch, halo rows read from the neighbour CTA over distributed shared
  *                   memory, one hardware cluster barrier per step (for launch-latency-bound decks: 128 x 128 and

@@ -4,8 +4,8 @@
 // bandwidth again (profiles/r02_summary.md): the only way further is to touch DRAM even less often.  This kernel is
 // the same scheme with a chain of K steps: a warp walks down a strip of 128 aligned columns (120 owned, 4 halo
 // columns per side -- exactly what FOUR steps consume, one column per side and step), and row r of the walk runs
-//   step 1 of row r        out of the staging row that cp.async filled two rows ahead,
-//   step 2 of row r-1      out of ring 1 (three rows of step-1 results in shared memory),
+//   step 1 of row r        out of the staging row that cp.async filled D = 1 or 2 rows ahead,
+//   step 2 of row r-1      out of ring 1 (the step-1 results the second step still needs, in shared memory),
 //   ...
 //   step K of row r-K+1    out of ring K-1, stored to the other buffer (lanes 1..30).
 // Per cell and K steps 36 B are read and 36 B written (+6.7 % redundant columns, +2(K-1)/band_rows redundant rows).
@@ -16,10 +16,15 @@
 // The arithmetic per cell and step is collide()/accelerate() of lbm_cell.cuh: bit-identical to K launches of
 // step_vec4 and to the oracle.
 //
+// Launch shape: ONE warp per CTA, as many CTAs per SM as its shared memory holds (K = 3, D = 1: eleven) -- an SM slot
+// is free again the moment a work item ends; the per-step sums leave the kernel as one fp64 partial per warp.  K = 3
+// with one staging row is the automatic choice wherever a fused kernel runs (183-190 GLUPS at 16384^2 on one B200,
+// DRAM at 0.72 of the copy peak, bound by the FMA pipe; profiles/r02_fused2.md, profiles/r02_summary.md).
+//
 // Ring slabs (PEER): every slab keeps kHalo = 4 halo rows per side, all nine planes (padded rows: 0 and rows+1 next
 // to the slab, rows+2(d-1) / rows+2(d-1)+1 the southern / northern neighbour's row d rows away, d = 2..4).  The
 // steps before the last are ALSO computed for the neighbours' rows they need (from the halo rows), so a pass needs no
-// exchange in the middle.  Once per pass the items of the two edge bands store their final rows 0..3 and rows-4..
+// exchange in the middle.  Once per pass the items of the two edge bands copy their final rows 0..3 and rows-4..
 // rows-1 into the neighbours' halo rows over NVLink and publish one flag word per strip and direction, after having
 // waited for the neighbours' words of strips c-1, c, c+1 -- the protocol of kernel 5, with a deeper halo.
 #pragma once

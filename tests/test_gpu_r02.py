@@ -197,7 +197,7 @@ def test_cluster_kernel_is_the_default_for_the_small_decks_only(pkg):
         assert sim.get_option("kernel") != 6
 
 
-@pytest.mark.parametrize("steps,stage_rows", [(3, 1), (3, 2), (4, 1), (4, 2)])
+@pytest.mark.parametrize("steps,stage_rows", [(2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2)])
 @pytest.mark.parametrize("shape,band", [((500, 77), 0), ((500, 77), 5), ((240, 9), 0), ((1024, 40), 7), ((368, 130), 64)])
 def test_k_steps_per_pass_kernel_is_bit_identical(pkg, oracle, steps, stage_rows, shape, band):
     """Kernel 7 (three / four timesteps per pass over HBM): random obstacles on every edge (x- and y-wrap), an
@@ -212,9 +212,12 @@ def test_k_steps_per_pass_kernel_is_bit_identical(pkg, oracle, steps, stage_rows
     ref_av = oracle.run(ref, obstacles, sum(runs), DENSITY, ACCEL, OMEGA, pkg.free_cells_inv(obstacles))
     with pkg.Simulation(nx, ny, DENSITY, ACCEL, OMEGA, obstacles, device=0) as sim:
         sim.set_option("fused2", 1)
+        sim.set_option("fused_k7", 1)                      # kernel 7 also for two steps per pass (default: kernel 5)
         sim.set_option("fused_steps", steps)
         sim.set_option("fused_deep", stage_rows - 1)       # one or two staging rows (copies one / two rows ahead)
         sim.set_option("band_rows", band)
+        if band == 5:
+            sim.set_option("fused_ctas", 1)                # all resident warps in ONE CTA instead of one warp per CTA
         assert sim.get_option("kernel") == 7 and sim.get_option("fused_steps") == steps
         sim.set_cells(cells0)
         av = np.concatenate([sim.run(n) for n in runs])
