@@ -797,7 +797,7 @@ int enqueue_step(lbm_b200* h, int slot, bool fold_accel)
 
 // Two timesteps in one pass over HBM (kernel 5): partial slots `slot` and `slot`+1 -- or, with `single`, the odd
 // last step of a run on a ring through the same strips (so that the strip-level handshake stays the only protocol
-// in use and the neighbours' two halo rows are refreshed).
+// in use and the neighbours' halo rows are refreshed).
 // The kernel needs more dynamic shared memory than the default limit: the opt-in is per device (context) and is
 // made once per slab when the kernel is first launched for it (Slab::fused_attr), never from process-global state.
 int allow_fused_smem(Slab& s)
@@ -1526,9 +1526,10 @@ int lbm_b200_enqueue(lbm_b200* h, int iters)
       h->launches++;
     }
     if (h->fused2 && h->n_ranks > 1) {
-      // The slab north of the driven row's owner recomputes that owner's last row in the first step of a pass and
-      // pulls planes 5 and 6 of the driven row out of its own second halo row: its copy (planes 2,3,5,6,7, pushed
-      // un-forced at the end of the last run) gets the same pre-pass; same inputs, same bits.
+      // The slab north of the driven row's owner recomputes the owner's last row(s) in the steps before the last of
+      // a pass and pulls the driven row out of its own second halo row (kernel 5: planes 5 and 6 of it; kernel 7: the
+      // whole row, which it recomputes as its row -2): its copy -- pushed un-forced at the end of the last run --
+      // gets the same pre-pass; same inputs, same bits.
       for (Slab& s : h->slabs) {
         if (s.first_row != 0) continue;
         CUDA_TRY(cudaSetDevice(s.device));
