@@ -377,7 +377,10 @@ void plan_bands_k(int rows, int nx, int band_rows, int sms, int k, int warps_per
       const double fill = (double)nb * strips / (double)slots;
       // (k >= 3: + the walk's start-up and drain -- 192-row bands measured 1.7 % faster than 128 at 16384^2, k = 4)
       const double over = 2.0 * (k - 1) + (k >= 3 ? 4.0 : 0.5);
-      const double cost = (per_b + over) * (fill > 1.0 ? fill + 0.62 : 1.37 * std::max(0.63, fill));
+      // (kernel 7 pays more for a launch whose items all start at once: 4096^2, K = 3: 128-row bands -- 0.69 of a
+      // wave -- 147.3 GLUPS, 24..32-row bands 157.5)
+      const double at_once = (k >= 3) ? 1.55 : 1.37;
+      const double cost = (per_b + over) * (fill > 1.0 ? fill + 0.62 : at_once * std::max(0.63, fill));
       if (want <= 0 || cost < best) { best = cost; want = b; }
     }
   }
