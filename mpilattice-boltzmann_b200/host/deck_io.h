@@ -30,7 +30,8 @@ static void die(const char* message, const int line, const char* file)
   exit(EXIT_FAILURE);
 }
 
-static void usage(const char* exe)
+/* (the launcher d2q9-bgk-mp has its own usage line with -np) */
+static void __attribute__((unused)) usage(const char* exe)
 {
   fprintf(stderr, "Usage: %s <paramfile> <obstaclefile>\n", exe);
   exit(EXIT_FAILURE);
