@@ -58,6 +58,11 @@ int lbm_b200_decompose(int ny, int n_slabs, int* rows, int* first_row);
  * band_rows = 0 picks the height automatically for a device with `sms` multiprocessors. */
 int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands, int* rows_per_band);
 
+/* The same for `steps` = 2..4 timesteps per pass in the default launch shape (2: kernel 5; 3, 4: kernel 7 with one
+ * staging row and one warp per CTA) and, with ring != 0, for a slab of a multi-GPU ring: its first and last band then
+ * hold at least the four rows kernel 7 pushes per direction from one work item (two for kernel 5). */
+int lbm_b200_plan_bands_ex(int rows, int nx, int band_rows, int sms, int steps, int ring, int* bands, int* rows_per_band);
+
 /* 1.0f / (number of unblocked cells), replacing d2q9-bgk.c:805, 945-950. */
 float lbm_b200_free_cells_inv(const int* obstacles, long n_cells);
 

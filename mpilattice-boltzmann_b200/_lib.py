@@ -21,6 +21,7 @@ SIGNATURES = {
     "lbm_b200_abi_version": (ctypes.c_int, []),
     "lbm_b200_decompose": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_int_p, c_int_p]),
     "lbm_b200_plan_bands": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p]),
+    "lbm_b200_plan_bands_ex": (ctypes.c_int, [ctypes.c_int] * 6 + [c_int_p, c_int_p]),
     "lbm_b200_free_cells_inv": (ctypes.c_float, [c_int_p, ctypes.c_long]),
     "lbm_b200_last_error": (ctypes.c_char_p, []),
     "lbm_b200_device_count": (ctypes.c_int, []),

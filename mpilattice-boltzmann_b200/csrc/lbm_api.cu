@@ -1182,6 +1182,18 @@ int lbm_b200_plan_bands(int rows, int nx, int band_rows, int sms, int* bands_out
   return LBM_B200_OK;
 }
 
+int lbm_b200_plan_bands_ex(int rows, int nx, int band_rows, int sms, int steps, int ring, int* bands_out, int* rows_per_band)
+{
+  if (rows < 2 || nx < 4 || sms < 1 || band_rows < 0 || steps < 2 || steps > lbm::kHalo || !bands_out || !rows_per_band)
+    return fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_plan_bands_ex");
+  if (ring && steps >= 3 && rows < lbm::kHalo + 2)
+    return fail(LBM_B200_ERR_ARG, "a ring slab needs at least %d rows for %d timesteps per pass", lbm::kHalo + 2, steps);
+  int wpc = 0, ctas = 0;
+  if (steps >= 3) stepsk_shape(steps, 1, &wpc, &ctas);
+  plan_bands_k(rows, nx, band_rows, sms, steps, steps >= 3 ? wpc * ctas : 12, ring != 0, bands_out, rows_per_band);
+  return LBM_B200_OK;
+}
+
 float lbm_b200_free_cells_inv(const int* obstacles, long n_cells)
 {
   if (!obstacles || n_cells < 0) { fail(LBM_B200_ERR_ARG, "bad arguments to lbm_b200_free_cells_inv"); return 0.0f; }

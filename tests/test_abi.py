@@ -90,6 +90,34 @@ def test_bad_arguments_are_rejected_before_any_device_work(pkg):
         pkg.Simulation(16, 16, 0.1, 0.005, 0.0, np.zeros((16, 16), np.int32))
 
 
+def test_band_plan_for_k_steps_and_ring_slabs(pkg):
+    """lbm_b200_plan_bands_ex: every row in exactly one band for K = 2..4; on a ring the first and the last band hold
+    the rows one work item pushes (two for kernel 5, four for kernel 7); the automatic heights of the default kernel
+    (K = 3) stay inside the measured optima (profiles/r02_fused2.md, section 8)."""
+    lib = pkg.library()
+
+    def plan(rows, nx, want, steps, ring, sms=148):
+        bands, per = ctypes.c_int(), ctypes.c_int()
+        assert lib.lbm_b200_plan_bands_ex(rows, nx, want, sms, steps, ring, ctypes.byref(bands), ctypes.byref(per)) == 0
+        return bands.value, per.value
+
+    for steps in (2, 3, 4):
+        for ring in (0, 1):
+            edge = (4 if steps >= 3 else 2) if ring else (1 if steps >= 3 else 2)
+            for rows in list(range(6, 70)) + [127, 128, 129, 2048, 16384]:
+                for want in (0, 1, 3, 4, 5, 8, 64, 1000):
+                    bands, per = plan(rows, 1024, want, steps, ring)
+                    last = rows - (bands - 1) * per
+                    assert bands >= 1 and per >= 1 and 0 < last <= max(per, rows), (steps, ring, rows, want)
+                    if bands > 1:
+                        assert per >= edge and last >= edge, (steps, ring, rows, want, bands, per)
+    assert plan(16384, 16384, 0, 3, 0)[1] in (96, 128, 160, 192) and plan(2048, 16384, 0, 3, 1)[1] in (24, 48)
+    assert plan(4096, 4096, 0, 3, 0)[1] in (24, 32) and plan(2048, 2048, 0, 3, 0)[1] in (24, 32)
+    bands, per = ctypes.c_int(), ctypes.c_int()
+    assert lib.lbm_b200_plan_bands_ex(5, 1024, 0, 148, 3, 1, ctypes.byref(bands), ctypes.byref(per)) != 0   # a ring slab that thin
+    assert lib.lbm_b200_plan_bands_ex(64, 1024, 0, 148, 5, 0, ctypes.byref(bands), ctypes.byref(per)) != 0
+
+
 def test_band_plan_of_the_fused_kernel(pkg):
     """Every row belongs to exactly one band, all bands but the last are equally tall, the first and the last hold
     at least two rows (ring slabs push two rows per direction from one work item); the automatic height stays inside
